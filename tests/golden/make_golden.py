@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ (run in the dev container only).
+
+Sources of truth, none of them modified:
+  * /root/reference/loss.py            -> loss.npz   (photometric / ncc / smoothness / OFEloss)
+  * /root/reference/models.py          -> warps.npz  (opticalFlowReg.stn)
+  * /root/reference/PWC/models/PWCNet.py -> warps.npz (PWCDCNet.warp)
+  * TVM's numpy ``correlation_nchw_python`` (ships in this image's site-packages) -> corr.npz
+  * torch ``F.grid_sample(padding_mode='border', align_corners=True)``           -> resample.npz
+
+The reference modules need a few absent third-party imports stubbed (monai,
+matplotlib, skimage, torchmetrics, RAFT, the custom CUDA layers); the stubs are
+empty modules, the reference functions that run are untouched.  Two module
+globals are redirected for a GPU-less host: ``loss.device`` (cuda -> cpu) and,
+while ``PWCDCNet.warp`` runs, ``Tensor.cuda`` (identity).
+
+    python tests/golden/make_golden.py      # rewrites the .npz files next to this script
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _install_stubs():
+    class _Anything:  # attribute sink for "from x import y"
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return _Anything()
+
+        def __getattr__(self, k):
+            return _Anything()
+
+    for name in ["monai", "monai.data", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "skimage",
+                 "skimage.measure", "torchmetrics", "torchmetrics.functional",
+                 "torchmetrics.functional.clustering", "torchmetrics.functional.regression",
+                 "RAFT", "RAFT.core", "RAFT.core.raft", "cv2"]:
+        m = _stub(name)
+        def _ga(k, _A=_Anything):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return _A()
+        m.__getattr__ = _ga  # type: ignore
+        m.__path__ = []  # behave as a package
+    sys.modules["monai.data"].MetaTensor = torch.Tensor
+    for name in ["correlation_package", "correlation_package.correlation",
+                 "networks", "networks.resample2d_package", "networks.resample2d_package.resample2d",
+                 "networks.channelnorm_package", "networks.channelnorm_package.channelnorm",
+                 "flownet2.networks.correlation_package", "flownet2.networks.correlation_package.correlation",
+                 "flownet2.networks.resample2d_package", "flownet2.networks.resample2d_package.resample2d",
+                 "flownet2.networks.channelnorm_package", "flownet2.networks.channelnorm_package.channelnorm"]:
+        m = _stub(name)
+        m.__path__ = []
+        m.Correlation = m.Resample2d = m.ChannelNorm = torch.nn.Identity
+
+
+def main():
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "PWC", "models"))
+    _install_stubs()
+    g = torch.Generator().manual_seed(6)  # the reference's training seed (train.py:122)
+
+    # ------------------------------------------------------------------ loss.py
+    ref_loss = importlib.import_module("loss")
+    ref_loss.device = torch.device("cpu")
+    B = 3
+    fixed = torch.rand(B, 1, 32, 32, generator=g)
+    scales = [(32, 32), (16, 16), (8, 8), (4, 4)]
+    flows = [torch.randn(B, 2, h, w, generator=g) * 1.5 for h, w in scales]
+    warped = [torch.rand(B, 1, h, w, generator=g) for h, w in scales]
+    out = {"fixed": fixed.numpy()}
+    for i, (fl, wp) in enumerate(zip(flows, warped)):
+        out[f"flow{i}"] = fl.numpy()
+        out[f"warped{i}"] = wp.numpy()
+        out[f"photo{i}"] = ref_loss.photometric_loss(fixed, wp).numpy()
+        out[f"ncc{i}"] = ref_loss.correlation_loss(fixed, wp).numpy()
+        out[f"smooth{i}"] = ref_loss.smoothness_loss(fl).numpy()
+    p, c, s, tot = ref_loss.OFEloss(flows, warped, fixed)
+    out["ofe"] = np.array([p.item(), c.item(), s.item(), tot.item()], dtype=np.float64)
+    p, c, s, tot = ref_loss.OFEloss(flows[:2], warped[:2], fixed, lamb_da=0.25, gamma=10.0, zeta=3.0)
+    out["ofe_alt"] = np.array([p.item(), c.item(), s.item(), tot.item()], dtype=np.float64)
+    # degenerate NCC branch (loss.py:59-60): exactly-representable constant image -> corr = 1 -> loss 0
+    const = torch.full((B, 1, 16, 16), 0.5)
+    out["ncc_const"] = ref_loss.correlation_loss(fixed, const).numpy()
+    out["smooth_zero"] = ref_loss.smoothness_loss(torch.zeros(B, 2, 8, 8)).numpy()
+    # gradients of the total w.r.t. warped / flow (autograd through the reference code)
+    fl_g = [f.clone().requires_grad_(True) for f in flows]
+    wp_g = [w.clone().requires_grad_(True) for w in warped]
+    tot = ref_loss.OFEloss(fl_g, wp_g, fixed)[3]
+    tot.backward()
+    for i in range(len(scales)):
+        out[f"gflow{i}"] = fl_g[i].grad.numpy()
+        out[f"gwarped{i}"] = wp_g[i].grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+
+    # ------------------------------------------------------------------ warps
+    ref_models = importlib.import_module("models")
+    stn = ref_models.opticalFlowReg.stn
+    ref_pwc = importlib.import_module("PWCNet")
+    out = {}
+    frame = torch.rand(2, 1, 24, 24, generator=g)
+    for tag, (h, w) in {"a": (24, 24), "b": (12, 12), "c": (6, 10)}.items():
+        flow = torch.randn(2, 2, h, w, generator=g) * 2.5
+        out[f"stn_flow_{tag}"] = flow.numpy()
+        out[f"stn_out_{tag}"] = stn(None, flow, frame).numpy()
+    out["stn_frame"] = frame.numpy()
+    out["stn_zero"] = stn(None, torch.zeros(1, 2, 8, 8), frame[:1, :, :8, :8].contiguous()).numpy()
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for tag, (C, h, w) in {"a": (5, 16, 16), "b": (3, 9, 13)}.items():
+            x = torch.randn(2, C, h, w, generator=g)
+            flo = torch.randn(2, 2, h, w, generator=g) * 2.0
+            out[f"pwc_x_{tag}"] = x.numpy()
+            out[f"pwc_flow_{tag}"] = flo.numpy()
+            out[f"pwc_out_{tag}"] = ref_pwc.PWCDCNet.warp(None, x, flo).numpy()
+        x = torch.rand(1, 1, 8, 8, generator=g)
+        out["pwc_zero_x"] = x.numpy()
+        out["pwc_zero_out"] = ref_pwc.PWCDCNet.warp(None, x, torch.zeros(1, 2, 8, 8)).numpy()
+    finally:
+        torch.Tensor.cuda = real_cuda
+    np.savez_compressed(os.path.join(HERE, "warps.npz"), **out)
+
+    # ------------------------------------------------------------------ correlation (TVM numpy)
+    sys.path.insert(0, "/opt/prime-rl/.venv/lib/python3.12/site-packages/tilelang/3rdparty/tvm/python/tvm/topi/testing")
+    tvm_corr = importlib.import_module("correlation_nchw_python").correlation_nchw_python
+    out = {}
+    cases = {  # tag: (B,C,H,W, pad,k,md,s1,s2)
+        "pwc": (2, 6, 7, 9, 4, 1, 4, 1, 1),       # PWCNet.py:69
+        "fnc": (1, 5, 6, 8, 20, 1, 20, 1, 2),     # FlowNetC.py:31
+        "k3": (1, 3, 9, 10, 3, 3, 2, 1, 1),       # general kernel_size (Caffe window convention)
+        "s1": (1, 4, 12, 12, 4, 1, 4, 2, 2),      # stride1 > 1 with an exactly divisible extent
+    }
+    for tag, (B_, C_, H_, W_, pad, k, md, s1, s2) in cases.items():
+        a = torch.randn(B_, C_, H_, W_, generator=g).numpy()
+        b = torch.randn(B_, C_, H_, W_, generator=g).numpy()
+        out[f"{tag}_f1"] = a
+        out[f"{tag}_f2"] = b
+        out[f"{tag}_params"] = np.array([pad, k, md, s1, s2])
+        out[f"{tag}_out"] = tvm_corr(a.astype(np.float64), b.astype(np.float64), k, md, s1, s2, pad, True)
+    np.savez_compressed(os.path.join(HERE, "corr.npz"), **out)
+
+    # ------------------------------------------------------------------ resample2d (grid_sample border)
+    out = {}
+    for tag, (B_, C_, H_, W_) in {"a": (2, 3, 17, 23), "b": (1, 1, 8, 8)}.items():
+        img = torch.randn(B_, C_, H_, W_, generator=g, dtype=torch.float64)
+        flow = torch.randn(B_, 2, H_, W_, generator=g, dtype=torch.float64) * 6.0
+        xs = torch.arange(W_, dtype=torch.float64).view(1, 1, W_) + flow[:, 0]
+        ys = torch.arange(H_, dtype=torch.float64).view(1, H_, 1) + flow[:, 1]
+        grid = torch.stack((2 * xs / (W_ - 1) - 1, 2 * ys / (H_ - 1) - 1), dim=-1)
+        res = F.grid_sample(img, grid, mode="bilinear", padding_mode="border", align_corners=True)
+        out[f"{tag}_in1"] = img.numpy().astype(np.float32)
+        out[f"{tag}_flow"] = flow.numpy().astype(np.float32)
+        # recompute from the float32-rounded inputs so fixture in/out are consistent
+        img32 = torch.from_numpy(out[f"{tag}_in1"]).double()
+        fl32 = torch.from_numpy(out[f"{tag}_flow"]).double()
+        xs = torch.arange(W_, dtype=torch.float64).view(1, 1, W_) + fl32[:, 0]
+        ys = torch.arange(H_, dtype=torch.float64).view(1, H_, 1) + fl32[:, 1]
+        grid = torch.stack((2 * xs / (W_ - 1) - 1, 2 * ys / (H_ - 1) - 1), dim=-1)
+        out[f"{tag}_out"] = F.grid_sample(img32, grid, mode="bilinear", padding_mode="border",
+                                          align_corners=True).numpy()
+    np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
+    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+
+
+if __name__ == "__main__":
+    main()
