@@ -1,0 +1,152 @@
+/*
+ * ofr_b200.h -- C ABI of the B200 (sm_100a) optical-flow registration hot path.
+ *
+ * One shared library (libofr_b200.so) exports every entry point below with C
+ * linkage.  Signatures carry only plain pointers, ints, doubles and an opaque
+ * stream handle (a cudaStream_t / CUstream passed as void*): no torch types, no
+ * C++ types.  This is the boundary a maintainer of the reference binds instead
+ * of the pybind11 modules `correlation_cuda`, `resample2d_cuda`,
+ * `channelnorm_cuda` of NVIDIA/flownet2-pytorch that the reference imports
+ * (flownet2/networks/FlowNetC.py:8, flownet2/models.py:10-11,
+ * PWC/models/PWCNet.py:13) and instead of the eager-PyTorch code of
+ * models.py:256-268 (stn), PWC/models/PWCNet.py:143-179 (warp) and
+ * loss.py:9-84 (OFEloss).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Contract:
+ *  - every tensor is float32, NCHW, contiguous, resident on the current device;
+ *  - the caller owns all memory (inputs, outputs, gradients, workspaces); the
+ *    library never allocates device memory, never frees, never keeps a pointer;
+ *  - outputs are fully overwritten (no "pre-zeroed" assumption);
+ *  - calls are asynchronous on `stream`, re-entrant, hold no mutable global
+ *    state, never synchronise the host and are CUDA-graph capturable;
+ *  - return value: 0 on success; OFR_E* (< 1000) for argument errors detected
+ *    on the host before any launch; 1000 + cudaError_t for CUDA failures.
+ *    Nothing throws across the ABI.  There is no CPU fallback.
+ */
+#ifndef OFR_B200_H
+#define OFR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFR_ABI_VERSION 1
+
+typedef void* ofr_stream_t; /* cudaStream_t */
+
+enum {
+    OFR_OK = 0,
+    OFR_EINVAL = 1,     /* null pointer / non-positive dimension / bad enum        */
+    OFR_ENOTSUP = 2,    /* legal but unimplemented parameter combination           */
+    OFR_EWORKSPACE = 3, /* workspace missing, too small or misaligned (256 B)      */
+    OFR_ECUDA = 1000    /* 1000 + cudaError_t                                      */
+};
+
+/* Version of this ABI (OFR_ABI_VERSION the library was built with). */
+int ofr_abi_version(void);
+/* Static, human readable text for a return code (never NULL). */
+const char* ofr_error_string(int code);
+/* Number of kernels this library has launched in the calling process since load
+ * (monotonic, relaxed atomic; used by bench.py for its "gpu_launches" claim). */
+uint64_t ofr_launch_count(void);
+
+/* ------------------------------------------------------------------ Correlation
+ * Replaces Correlation(pad_size, kernel_size, max_displacement, stride1, stride2,
+ * corr_multiply).forward/backward -- ctor sites flownet2/networks/FlowNetC.py:28,31
+ * and PWC/models/PWCNet.py:69; call sites FlowNetC.py:88, PWCNet.py:200-259;
+ * alias FlowNetS/util.py:58-72 (spatial_correlation_sample(...)/C).
+ *
+ *   out[b,(tj+r)*D+(ti+r),y,x] = 1/(k*k*C) * sum_{c,h,w<k}
+ *        P1[b,c,y1+h,x1+w] * P2[b,c,y1+tj*s2+h, x1+ti*s2+w]
+ *   P = input zero-padded by `pad`, y1 = y*s1+md, r = md/s2, D = 2r+1,
+ *   Hout = ceil((H + 2*pad - 2*(md + (k-1)/2)) / s1).
+ * corr_multiply is accepted by the Python module and ignored (always a product).
+ */
+int ofr_corr_out_shape(int H, int W, int pad, int k, int md, int s1, int s2,
+                       int* D, int* Hout, int* Wout);
+int ofr_corr_fwd(const float* f1, const float* f2, float* out,
+                 int B, int C, int H, int W,
+                 int pad, int k, int md, int s1, int s2, ofr_stream_t stream);
+/* gI1 / gI2 may each be NULL to skip that gradient. */
+int ofr_corr_bwd(const float* f1, const float* f2, const float* gO,
+                 float* gI1, float* gI2,
+                 int B, int C, int H, int W,
+                 int pad, int k, int md, int s1, int s2, ofr_stream_t stream);
+
+/* ------------------------------------------------------------------ Resample / warps
+ * One kernel family, three sampling conventions:
+ *  OFR_WARP_FLOWNET2 : Resample2d(kernel_size=1, bilinear=True) -- flownet2/models.py:52,139..176.
+ *                      sample (x+u, y+v) in pixels, taps clamped to the image.
+ *  OFR_WARP_FLOWNET2_NEAREST : Resample2d(bilinear=False), nearest tap, clamped.
+ *  OFR_WARP_STN      : opticalFlowReg.stn -- models.py:256-268 (after its F.interpolate):
+ *                      g=(p+flow)*(2/W,2/H)-1, grid_sample(zeros, align_corners=True).
+ *  OFR_WARP_PWC      : PWCDCNet.warp -- PWC/models/PWCNet.py:143-179:
+ *                      g=2(p+flow)/max(W-1,1)-1, grid_sample(zeros, align_corners=False),
+ *                      result zeroed where the warped ones-mask < 0.9999.
+ * in1 [B,C,Hin,Win], flow [B,2,Hf,Wf], out [B,C,Hf,Wf].  STN and PWC need Hin==Hf, Win==Wf.
+ */
+enum {
+    OFR_WARP_FLOWNET2 = 0,
+    OFR_WARP_STN = 1,
+    OFR_WARP_PWC = 2,
+    OFR_WARP_FLOWNET2_NEAREST = 3
+};
+int ofr_resample_fwd(const float* in1, const float* flow, float* out,
+                     int B, int C, int Hin, int Win, int Hf, int Wf,
+                     int mode, ofr_stream_t stream);
+/* Bytes of scratch ofr_resample_bwd needs when gI1 != NULL (0 when only gI2 is wanted). */
+size_t ofr_resample_bwd_workspace(int B, int C, int Hin, int Win, int Hf, int Wf, int mode);
+/* Deterministic backward.  gI1 [B,C,Hin,Win] and/or gI2 [B,2,Hf,Wf]; either may be NULL.
+ * The adjoint scatter into gI1 is run as a cell-binned gather in a fixed order
+ * (bitwise reproducible), not with floating-point atomics.  `ws` must be 256-byte
+ * aligned; its contents on entry are ignored. */
+int ofr_resample_bwd(const float* in1, const float* flow, const float* gO,
+                     float* gI1, float* gI2,
+                     int B, int C, int Hin, int Win, int Hf, int Wf, int mode,
+                     void* ws, size_t ws_bytes, ofr_stream_t stream);
+
+/* ------------------------------------------------------------------ ChannelNorm
+ * Replaces ChannelNorm().forward/backward -- flownet2/models.py:40,141..180.
+ *   out[b,0,y,x] = sqrt(sum_c x[b,c,y,x]^2);   gI = gO * x / (out + 1e-8).
+ */
+int ofr_chnorm_fwd(const float* x, float* out, int B, int C, int H, int W, ofr_stream_t stream);
+int ofr_chnorm_bwd(const float* x, const float* out, const float* gO, float* gI,
+                   int B, int C, int H, int W, ofr_stream_t stream);
+
+/* ------------------------------------------------------------------ Self-supervised loss
+ * Replaces OFEloss and its three terms -- loss.py:9-13 (photometric), :23-35
+ * (smoothness, Charbonnier), :52-64 (global NCC), :66-84 (multi-scale weights).
+ * `fixed` is the full-resolution fixed image [B,1,Hs,Ws]; its bilinear
+ * (align_corners=False) resize to each scale is done inside the kernel.
+ * All reductions accumulate in float64 in a fixed order (bitwise reproducible).
+ */
+#define OFR_LOSS_MAX_SCALES 8
+#define OFR_LOSS_STATE_DOUBLES 16 /* per scale, see loss.cu for the slot layout */
+typedef struct {
+    const float* warped; /* [B,1,h,w]                       */
+    const float* flow;   /* [B,2,h,w]                       */
+    float* g_warped;     /* backward only: [B,1,h,w] or NULL */
+    float* g_flow;       /* backward only: [B,2,h,w] or NULL */
+    int h, w;
+} ofr_loss_scale_t;
+size_t ofr_loss_workspace(int n_scales);
+/* out4 (device, 4 doubles) <- (photometric, ncc, smoothness, total) exactly as OFEloss
+ * returns them; state (device, n*OFR_LOSS_STATE_DOUBLES doubles) <- moments kept for backward. */
+int ofr_loss_fwd(const float* fixed, int B, int Hs, int Ws,
+                 const ofr_loss_scale_t* scales, int n_scales,
+                 double lamb_da, double gamma, double zeta,
+                 double* out4, double* state,
+                 void* ws, size_t ws_bytes, ofr_stream_t stream);
+/* grad4 (device, 4 doubles) = upstream gradients of (photometric, ncc, smoothness, total). */
+int ofr_loss_bwd(const float* fixed, int B, int Hs, int Ws,
+                 const ofr_loss_scale_t* scales, int n_scales,
+                 double lamb_da, double gamma, double zeta,
+                 const double* grad4, const double* state, ofr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFR_B200_H */

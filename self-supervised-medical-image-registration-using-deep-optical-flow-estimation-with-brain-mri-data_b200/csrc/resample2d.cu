@@ -1,0 +1,647 @@
+// Bilinear warps: Resample2d (flownet2), opticalFlowReg.stn and PWCDCNet.warp in one kernel family.
+//
+// Reference semantics:
+//   FLOWNET2 : flownet2/models.py:139,151,163,176  sample (x+u, y+v), taps clamped, fractional weights unclamped
+//   STN      : models.py:256-268                   g=(p+f)*(2/W,2/H)-1, grid_sample(zeros, align_corners=True)
+//   PWC      : PWC/models/PWCNet.py:143-179        g=2(p+f)/(W-1)-1, grid_sample(zeros, align_corners=False),
+//                                                  output zeroed where the warped ones-mask < 0.9999
+// The coordinate arithmetic is spelled with explicit round-to-nearest intrinsics in the
+// same operation order PyTorch uses, so that the float32 sampling positions agree with
+// the reference bit for bit (a 1-ulp difference in a normalised coordinate is 1.5e-5 px at W=512).
+//
+// Forward  : one thread per 4 consecutive output pixels (128-bit flow loads / output stores when
+//            Wf % 4 == 0), channel chunks on blockIdx.y.  Algorithmic bytes 4*B*Hf*Wf*(2C+2).
+// Backward : gI2 (flow) is a per-source gather + analytic derivative, channels split over the CTA's
+//            y-dimension and combined through shared memory in a fixed order.
+//            gI1 (image) is the adjoint scatter.  Upstream used float atomicAdd (non-deterministic);
+//            here every source pixel is binned by the top-left cell of its 2x2 footprint
+//            (integer atomics only: counts are order independent), the bins are turned into a CSR
+//            by an exclusive scan, and each *target* pixel then gathers from the <= 4 cells that can
+//            reach it, visiting the entries of a cell in ascending source index.  The floating-point
+//            summation order is therefore a function of the data only: bitwise reproducible.
+//            Cells holding more than kHeavy entries are sorted once by a CTA-wide bitonic network so
+//            the gather never does quadratic work on degenerate flows.
+#include "ofr_common.cuh"
+
+namespace {
+
+constexpr int kHeavy = 32;       // cells with more entries than this are pre-sorted
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct WarpGeom {
+    int B, C, Hin, Win, Hf, Wf;
+    float fx, fy;  // STN: float32(2/W), float32(2/H)
+};
+
+struct Samp {
+    float wx0, wx1, wy0, wy1;  // bilinear weights of the left/right and top/bottom taps
+    int x0, y0;                // floor of the sampling position, clamped to [-2, W] / [-2, H]
+    bool live;                 // false: contributes nothing (PWC mask) -> output 0, no gradient
+};
+
+__device__ __forceinline__ int safe_floor_int(float f, int hi) {
+    // clamp in float first so huge / NaN flows cannot overflow the int conversion
+    f = fminf(fmaxf(f, -2.f), (float)hi);
+    return (int)f;
+}
+
+template <int MODE>
+__device__ __forceinline__ Samp make_samp(int x, int y, float u, float v, const WarpGeom& g) {
+    Samp s;
+    float ix, iy;
+    if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) {
+        ix = __fadd_rn((float)x, u);
+        iy = __fadd_rn((float)y, v);
+    } else if (MODE == OFR_WARP_STN) {
+        float gx = __fsub_rn(__fmul_rn(__fadd_rn(u, (float)x), g.fx), 1.f);
+        float gy = __fsub_rn(__fmul_rn(__fadd_rn(v, (float)y), g.fy), 1.f);
+        ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(g.Win - 1));
+        iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(g.Hin - 1));
+    } else {  // PWC
+        const float dx = (float)max(g.Win - 1, 1), dy = (float)max(g.Hin - 1, 1);
+        float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)x, u)), dx), 1.f);
+        float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)y, v)), dy), 1.f);
+        ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.Win), 1.f), 2.f);
+        iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.Hin), 1.f), 2.f);
+    }
+    const float fxl = floorf(ix), fyl = floorf(iy);
+    if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) {
+        s.wx1 = __fsub_rn(ix, fxl);
+        s.wy1 = __fsub_rn(iy, fyl);
+        s.wx0 = __fsub_rn(1.f, s.wx1);
+        s.wy0 = __fsub_rn(1.f, s.wy1);
+    } else {  // grid_sample: nw = (ix_se - ix) * (iy_se - iy) ...
+        s.wx0 = __fsub_rn(__fadd_rn(fxl, 1.f), ix);
+        s.wx1 = __fsub_rn(ix, fxl);
+        s.wy0 = __fsub_rn(__fadd_rn(fyl, 1.f), iy);
+        s.wy1 = __fsub_rn(iy, fyl);
+    }
+    s.x0 = safe_floor_int(fxl, g.Win);
+    s.y0 = safe_floor_int(fyl, g.Hin);
+    s.live = true;
+    if (MODE == OFR_WARP_PWC) {
+        const bool xl = s.x0 >= 0 && s.x0 < g.Win, xr = s.x0 + 1 >= 0 && s.x0 + 1 < g.Win;
+        const bool yt = s.y0 >= 0 && s.y0 < g.Hin, yb = s.y0 + 1 >= 0 && s.y0 + 1 < g.Hin;
+        float m = 0.f;  // the warped ones-image, accumulated nw, ne, sw, se like grid_sample
+        if (xl && yt) m = __fadd_rn(m, __fmul_rn(s.wx0, s.wy0));
+        if (xr && yt) m = __fadd_rn(m, __fmul_rn(s.wx1, s.wy0));
+        if (xl && yb) m = __fadd_rn(m, __fmul_rn(s.wx0, s.wy1));
+        if (xr && yb) m = __fadd_rn(m, __fmul_rn(s.wx1, s.wy1));
+        s.live = m >= 0.9999f;
+    }
+    return s;
+}
+
+// Tap column/row for tap offset d in {0,1}: clamped (FLOWNET2) or -1 when outside (zeros padding).
+template <int MODE>
+__device__ __forceinline__ int tap_index(int i0, int d, int n) {
+    int t = i0 + d;
+    if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) return min(max(t, 0), n - 1);
+    return (t >= 0 && t < n) ? t : -1;
+}
+
+template <int MODE>
+struct Taps {
+    int xl, xr, yt, yb;
+    __device__ __forceinline__ Taps(const Samp& s, const WarpGeom& g) {
+        xl = tap_index<MODE>(s.x0, 0, g.Win);
+        xr = tap_index<MODE>(s.x0, 1, g.Win);
+        yt = tap_index<MODE>(s.y0, 0, g.Hin);
+        yb = tap_index<MODE>(s.y0, 1, g.Hin);
+    }
+    __device__ __forceinline__ float fetch(const float* __restrict__ img, int y, int x, int W) const {
+        return (x >= 0 && y >= 0) ? __ldg(img + (long long)y * W + x) : 0.f;
+    }
+};
+
+template <int MODE>
+__device__ __forceinline__ float bilerp(const float* __restrict__ img, const Samp& s, const Taps<MODE>& t, int W) {
+    float acc = __fmul_rn(__fmul_rn(s.wx0, s.wy0), t.fetch(img, t.yt, t.xl, W));
+    acc = fmaf(__fmul_rn(s.wx1, s.wy0), t.fetch(img, t.yt, t.xr, W), acc);
+    acc = fmaf(__fmul_rn(s.wx0, s.wy1), t.fetch(img, t.yb, t.xl, W), acc);
+    acc = fmaf(__fmul_rn(s.wx1, s.wy1), t.fetch(img, t.yb, t.xr, W), acc);
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int kFwdThreads = 256;
+constexpr int kFwdChunk = 8;  // channels per blockIdx.y slice
+
+template <int MODE, int PX>
+__global__ void __launch_bounds__(kFwdThreads) resample_fwd_kernel(const float* __restrict__ in1,
+                                                                   const float* __restrict__ flow,
+                                                                   float* __restrict__ out, WarpGeom g) {
+    const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
+    const long long total = (long long)g.B * hwf / PX;
+    const int c0 = blockIdx.y * kFwdChunk, c1 = min(c0 + kFwdChunk, g.C);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i * PX;
+        const int b = (int)(pix / hwf);
+        const int rem = (int)(pix - (long long)b * hwf);
+        const int y = rem / g.Wf, x = rem - y * g.Wf;
+        const float* fu = flow + (long long)b * 2 * hwf + rem;
+        float u[PX], v[PX];
+        if (PX == 4) {
+            float4 a = ofr::ldg4(fu), c = ofr::ldg4(fu + hwf);
+            u[0] = a.x, u[1 % PX] = a.y, u[2 % PX] = a.z, u[3 % PX] = a.w;
+            v[0] = c.x, v[1 % PX] = c.y, v[2 % PX] = c.z, v[3 % PX] = c.w;
+        } else {
+            u[0] = __ldg(fu);
+            v[0] = __ldg(fu + hwf);
+        }
+        Samp s[PX];
+#pragma unroll
+        for (int k = 0; k < PX; ++k) s[k] = make_samp<MODE>(x + k, y, u[k], v[k], g);
+        for (int c = c0; c < c1; ++c) {
+            const float* img = in1 + ((long long)b * g.C + c) * hwi;
+            float r[PX];
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+                if (MODE == OFR_WARP_FLOWNET2_NEAREST) {
+                    // nearest tap: floor(x + u + 0.5), clamped
+                    const float xn = floorf(__fadd_rn(__fadd_rn((float)(x + k), u[k]), 0.5f));
+                    const float yn = floorf(__fadd_rn(__fadd_rn((float)y, v[k]), 0.5f));
+                    const int xi = min(max(safe_floor_int(xn, g.Win), 0), g.Win - 1);
+                    const int yi = min(max(safe_floor_int(yn, g.Hin), 0), g.Hin - 1);
+                    r[k] = __ldg(img + (long long)yi * g.Win + xi);
+                } else {
+                    Taps<MODE> t(s[k], g);
+                    r[k] = s[k].live ? bilerp<MODE>(img, s[k], t, g.Win) : 0.f;
+                }
+            }
+            float* o = out + ((long long)b * g.C + c) * hwf + rem;
+            if (PX == 4)
+                ofr::stcs4(o, make_float4(r[0], r[1 % PX], r[2 % PX], r[3 % PX]));
+            else
+                o[0] = r[0];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Cell of a source pixel: top-left corner of its footprint, kx in [-1, Win-1], ky in [-1, Hin-1];
+// -1 when the source reaches no target at all.
+template <int MODE>
+__device__ __forceinline__ int cell_of(const Samp& s, const WarpGeom& g) {
+    if (!s.live) return -1;
+    int kx, ky;
+    if (MODE == OFR_WARP_FLOWNET2) {
+        kx = min(max(s.x0, -1), g.Win - 1);
+        ky = min(max(s.y0, -1), g.Hin - 1);
+    } else {
+        if (s.x0 < -1 || s.x0 > g.Win - 1 || s.y0 < -1 || s.y0 > g.Hin - 1) return -1;
+        kx = s.x0;
+        ky = s.y0;
+    }
+    return (ky + 1) * (g.Win + 1) + (kx + 1);
+}
+
+// Per-source pass: flow gradient (optional) and cell binning (optional).
+// blockDim = (32, CG): 32 consecutive source pixels, CG channel groups.
+template <int MODE, int CG, bool WANT_G2, bool WANT_BIN>
+__global__ void __launch_bounds__(32 * CG) resample_bwd_src_kernel(const float* __restrict__ in1,
+                                                                   const float* __restrict__ flow,
+                                                                   const float* __restrict__ gO,
+                                                                   float* __restrict__ gI2, int* __restrict__ counts,
+                                                                   int* __restrict__ key, int* __restrict__ rank,
+                                                                   WarpGeom g, float sx, float sy) {
+    __shared__ float red[2][CG][32];
+    const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
+    const long long total = (long long)g.B * hwf;
+    const long long pix = blockIdx.x * 32ll + threadIdx.x;
+    const bool in_range = pix < total;
+    int b = 0, rem = 0, y = 0, x = 0;
+    Samp s;
+    s.live = false;
+    if (in_range) {
+        b = (int)(pix / hwf);
+        rem = (int)(pix - (long long)b * hwf);
+        y = rem / g.Wf;
+        x = rem - y * g.Wf;
+        const float* fu = flow + (long long)b * 2 * hwf + rem;
+        s = make_samp<MODE>(x, y, __ldg(fu), __ldg(fu + hwf), g);
+    }
+    if (WANT_BIN && threadIdx.y == 0 && in_range) {
+        const int cell = cell_of<MODE>(s, g);
+        int r = 0;
+        if (cell >= 0) r = atomicAdd(counts + (long long)b * (g.Hin + 1) * (g.Win + 1) + cell, 1);
+        key[pix] = cell;
+        rank[pix] = r;
+    }
+    if (!WANT_G2) return;
+    float ax = 0.f, ay = 0.f;
+    if (in_range && s.live) {
+        Taps<MODE> t(s, g);
+        for (int c = threadIdx.y; c < g.C; c += CG) {
+            const float* img = in1 + ((long long)b * g.C + c) * hwi;
+            const float go = __ldg(gO + ((long long)b * g.C + c) * hwf + rem);
+            const float tl = t.fetch(img, t.yt, t.xl, g.Win), tr = t.fetch(img, t.yt, t.xr, g.Win);
+            const float bl = t.fetch(img, t.yb, t.xl, g.Win), br = t.fetch(img, t.yb, t.xr, g.Win);
+            // d out / d ix = wy0*(TR-TL) + wy1*(BR-BL);  d out / d iy = wx0*(BL-TL) + wx1*(BR-TR)
+            ax = fmaf(go, fmaf(s.wy1, br - bl, s.wy0 * (tr - tl)), ax);
+            ay = fmaf(go, fmaf(s.wx1, br - tr, s.wx0 * (bl - tl)), ay);
+        }
+    }
+    if (CG > 1) {
+        red[0][threadIdx.y][threadIdx.x] = ax;
+        red[1][threadIdx.y][threadIdx.x] = ay;
+        __syncthreads();
+        if (threadIdx.y == 0) {
+            ax = red[0][0][threadIdx.x];
+            ay = red[1][0][threadIdx.x];
+#pragma unroll
+            for (int k = 1; k < CG; ++k) {  // fixed order -> deterministic
+                ax += red[0][k][threadIdx.x];
+                ay += red[1][k][threadIdx.x];
+            }
+        }
+    }
+    if (threadIdx.y == 0 && in_range) {
+        float* o = gI2 + (long long)b * 2 * hwf + rem;
+        o[0] = ax * sx;
+        o[hwf] = ay * sy;
+    }
+}
+
+// ---- exclusive scan of the cell counts (three small kernels)
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) >= d) v += n;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int* __restrict__ counts,
+                                                                   int* __restrict__ blocksum, int n) {
+    __shared__ int wsum[kScanThreads / 32];
+    const int base = blockIdx.x * kScanTile;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        int i = base + k * kScanThreads + threadIdx.x;
+        if (i < n) s += counts[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < kScanThreads / 32; ++k) t += wsum[k];
+        blocksum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_top_kernel(int* __restrict__ blocksum, int nblk) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblk ? blocksum[i] : 0;
+        int incl = warp_incl_scan(v);
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = wsum[threadIdx.x];
+            int wi = warp_incl_scan(w);
+            wsum[threadIdx.x] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + wsum[threadIdx.x >> 5] + incl - v;
+        if (i < nblk) blocksum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int* __restrict__ counts,
+                                                                  const int* __restrict__ blocksum,
+                                                                  int* __restrict__ offsets, int n) {
+    __shared__ int wsum[kScanThreads / 32];
+    // each thread owns kScanItems consecutive elements so the scan order is the array order
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? counts[base + k] : 0;
+        s += v[k];
+    }
+    const int incl = warp_incl_scan(s);
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wpre = 0;
+    for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) wpre += wsum[k];
+    int run = blocksum[blockIdx.x] + wpre + incl - s;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) offsets[base + k] = run;
+        run += v[k];
+    }
+}
+
+// ---- CSR fill: entries[offset[cell] + rank] = source index within its image
+__global__ void __launch_bounds__(256) resample_fill_kernel(const int* __restrict__ key, const int* __restrict__ rank,
+                                                            const int* __restrict__ counts,
+                                                            const int* __restrict__ offsets, int* __restrict__ entries,
+                                                            int* __restrict__ heavy, int* __restrict__ heavy_n,
+                                                            long long total, int hwf, int cells_per_img) {
+    const long long pix = blockIdx.x * 256ll + threadIdx.x;
+    if (pix >= total) return;
+    const int k = key[pix];
+    if (k < 0) return;
+    const int b = (int)(pix / hwf);
+    const int cell = b * cells_per_img + k;
+    const int r = rank[pix];
+    entries[offsets[cell] + r] = (int)(pix - (long long)b * hwf);
+    if (r == 0 && counts[cell] > kHeavy) heavy[atomicAdd(heavy_n, 1)] = cell;
+}
+
+// ---- sort the entries of crowded cells (ascending).  One CTA per heavy cell, all-ascending bitonic
+// network ("flip" first step) so a virtual +inf padding beyond n never has to move.
+__global__ void __launch_bounds__(512) resample_sort_heavy_kernel(const int* __restrict__ heavy,
+                                                                  const int* __restrict__ heavy_n,
+                                                                  const int* __restrict__ counts,
+                                                                  const int* __restrict__ offsets,
+                                                                  int* __restrict__ entries) {
+    const int nh = *heavy_n;
+    for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+        const int cell = heavy[h];
+        const int n = counts[cell];
+        int* a = entries + offsets[cell];
+        int P = 1;
+        while (P < n) P <<= 1;
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+                    if (l > i && l < n) {
+                        const int vi = a[i], vl = a[l];
+                        if (vi > vl) {
+                            a[i] = vl;
+                            a[l] = vi;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ---- per-target gather of the adjoint.  Thread = one target pixel, blockIdx.y = channel chunk.
+constexpr int kTgtChunk = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __restrict__ flow,
+                                                               const float* __restrict__ gO,
+                                                               const int* __restrict__ counts,
+                                                               const int* __restrict__ offsets,
+                                                               const int* __restrict__ entries,
+                                                               float* __restrict__ gI1, WarpGeom g) {
+    const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
+    const long long tpix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tpix >= (long long)g.B * hwi) return;
+    const int b = (int)(tpix / hwi);
+    const int trem = (int)(tpix - (long long)b * hwi);
+    const int ty = trem / g.Win, tx = trem - ty * g.Win;
+    const int c0 = blockIdx.y * kTgtChunk;
+    const int nc = min(kTgtChunk, g.C - c0);
+    const int cw = g.Win + 1;
+    const long long cell_base = (long long)b * (g.Hin + 1) * cw;
+    const float* fl = flow + (long long)b * 2 * hwf;
+    const float* go = gO + ((long long)b * g.C + c0) * hwf;
+
+    float acc[kTgtChunk];
+#pragma unroll
+    for (int k = 0; k < kTgtChunk; ++k) acc[k] = 0.f;
+
+    // cells (ky, kx) in {ty-1, ty} x {tx-1, tx}; stored with a +1 bias
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ky = ty - 1 + (q >> 1), kx = tx - 1 + (q & 1);
+        const long long cell = cell_base + (long long)(ky + 1) * cw + (kx + 1);
+        const int n = counts[cell];
+        if (n == 0) continue;
+        const int* e = entries + offsets[cell];
+        int last = -1;
+        for (int it = 0; it < n; ++it) {
+            int src;
+            if (n == 1 || n > kHeavy) {
+                src = e[it];  // single entry, or pre-sorted by resample_sort_heavy_kernel
+            } else {          // next entry in ascending source order
+                src = 0x7fffffff;
+                for (int j = 0; j < n; ++j) {
+                    const int v = e[j];
+                    if (v > last && v < src) src = v;
+                }
+                last = src;
+            }
+            const int sy = src / g.Wf, sx = src - sy * g.Wf;
+            const Samp s = make_samp<MODE>(sx, sy, __ldg(fl + src), __ldg(fl + hwf + src), g);
+            const Taps<MODE> t(s, g);
+            // weight of each of the four taps if it lands on this target, else 0 (order TL, TR, BL, BR)
+            const float w0 = (t.xl == tx && t.yt == ty) ? __fmul_rn(s.wx0, s.wy0) : 0.f;
+            const float w1 = (t.xr == tx && t.yt == ty) ? __fmul_rn(s.wx1, s.wy0) : 0.f;
+            const float w2 = (t.xl == tx && t.yb == ty) ? __fmul_rn(s.wx0, s.wy1) : 0.f;
+            const float w3 = (t.xr == tx && t.yb == ty) ? __fmul_rn(s.wx1, s.wy1) : 0.f;
+#pragma unroll
+            for (int k = 0; k < kTgtChunk; ++k) {
+                if (k < nc) {
+                    const float gv = __ldg(go + (long long)k * hwf + src);
+                    float a = acc[k];
+                    a = fmaf(w0, gv, a);
+                    a = fmaf(w1, gv, a);
+                    a = fmaf(w2, gv, a);
+                    a = fmaf(w3, gv, a);
+                    acc[k] = a;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kTgtChunk; ++k)
+        if (k < nc) gI1[((long long)b * g.C + c0 + k) * hwi + trem] = acc[k];
+}
+
+// nearest mode: the flow gets no gradient; the image gradient is still a (deterministic) gather,
+// but no reference call site uses it -> not implemented.
+
+struct WsLayout {
+    size_t counts, misc, offsets, blocksum, key, rank, entries, heavy, total;
+    int ncell, nblk;
+    long long npix;
+};
+
+WsLayout ws_layout(int B, int Hin, int Win, int Hf, int Wf) {
+    WsLayout L;
+    L.ncell = B * (Hin + 1) * (Win + 1);
+    L.npix = (long long)B * Hf * Wf;
+    L.nblk = (L.ncell + kScanTile - 1) / kScanTile;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = ofr::align_up(o + bytes, 256);
+        return at;
+    };
+    L.counts = take(sizeof(int) * (size_t)L.ncell);
+    L.misc = take(256);
+    L.offsets = take(sizeof(int) * (size_t)L.ncell);
+    L.blocksum = take(sizeof(int) * (size_t)L.nblk);
+    L.key = take(sizeof(int) * (size_t)L.npix);
+    L.rank = take(sizeof(int) * (size_t)L.npix);
+    L.entries = take(sizeof(int) * (size_t)L.npix);
+    L.heavy = take(sizeof(int) * (size_t)(L.npix / kHeavy + 1));
+    L.total = o;
+    return L;
+}
+
+bool geom_ok(int B, int C, int Hin, int Win, int Hf, int Wf) {
+    if (B <= 0 || C <= 0 || Hin <= 0 || Win <= 0 || Hf <= 0 || Wf <= 0) return false;
+    // index arithmetic inside one image is 32-bit
+    if ((long long)Hf * Wf >= (1ll << 30) || (long long)(Hin + 1) * (Win + 1) >= (1ll << 30)) return false;
+    if ((long long)B * (Hin + 1) * (Win + 1) >= (1ll << 31)) return false;
+    return true;
+}
+
+WarpGeom make_geom(int B, int C, int Hin, int Win, int Hf, int Wf) {
+    WarpGeom g;
+    g.B = B, g.C = C, g.Hin = Hin, g.Win = Win, g.Hf = Hf, g.Wf = Wf;
+    g.fx = (float)(2.0 / Win);  // models.py:264 builds a FloatTensor from the python floats 2/w, 2/h
+    g.fy = (float)(2.0 / Hin);
+    return g;
+}
+
+template <int MODE>
+int launch_fwd(const float* in1, const float* flow, float* out, const WarpGeom& g, cudaStream_t st) {
+    const long long npix = (long long)g.B * g.Hf * g.Wf;
+    const unsigned gy = (unsigned)((g.C + kFwdChunk - 1) / kFwdChunk);
+    const bool vec = (g.Wf % 4 == 0) && ofr::aligned16(flow) && ofr::aligned16(out);
+    if (vec) {
+        dim3 grid(ofr::grid_for(npix / 4, kFwdThreads, 8), gy);
+        resample_fwd_kernel<MODE, 4><<<grid, kFwdThreads, 0, st>>>(in1, flow, out, g);
+    } else {
+        dim3 grid(ofr::grid_for(npix, kFwdThreads, 8), gy);
+        resample_fwd_kernel<MODE, 1><<<grid, kFwdThreads, 0, st>>>(in1, flow, out, g);
+    }
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+template <int MODE, int CG>
+int launch_src(const float* in1, const float* flow, const float* gO, float* gI2, int* counts, int* key, int* rank,
+               const WarpGeom& g, float sx, float sy, bool want_bin, cudaStream_t st) {
+    const long long npix = (long long)g.B * g.Hf * g.Wf;
+    dim3 block(32, CG), grid((unsigned)((npix + 31) / 32));
+    if (gI2 && want_bin)
+        resample_bwd_src_kernel<MODE, CG, true, true><<<grid, block, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
+    else if (gI2)
+        resample_bwd_src_kernel<MODE, CG, true, false><<<grid, block, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
+    else
+        resample_bwd_src_kernel<MODE, CG, false, true><<<grid, block, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+template <int MODE>
+int run_bwd(const float* in1, const float* flow, const float* gO, float* gI1, float* gI2, const WarpGeom& g,
+            void* ws, cudaStream_t st) {
+    // chain factors d(sample position)/d(flow), multiplied in the order autograd applies them
+    float sx = 1.f, sy = 1.f;
+    if (MODE == OFR_WARP_STN) {
+        sx = (0.5f * (float)(g.Win - 1)) * g.fx;
+        sy = (0.5f * (float)(g.Hin - 1)) * g.fy;
+    } else if (MODE == OFR_WARP_PWC) {
+        sx = (0.5f * (float)g.Win) / (float)max(g.Win - 1, 1) * 2.f;
+        sy = (0.5f * (float)g.Hin) / (float)max(g.Hin - 1, 1) * 2.f;
+    }
+    const bool want_bin = gI1 != nullptr;
+    WsLayout L = ws_layout(g.B, g.Hin, g.Win, g.Hf, g.Wf);
+    char* w = (char*)ws;
+    int* counts = want_bin ? (int*)(w + L.counts) : nullptr;
+    int* misc = want_bin ? (int*)(w + L.misc) : nullptr;
+    int* offsets = want_bin ? (int*)(w + L.offsets) : nullptr;
+    int* blocksum = want_bin ? (int*)(w + L.blocksum) : nullptr;
+    int* key = want_bin ? (int*)(w + L.key) : nullptr;
+    int* rank = want_bin ? (int*)(w + L.rank) : nullptr;
+    int* entries = want_bin ? (int*)(w + L.entries) : nullptr;
+    int* heavy = want_bin ? (int*)(w + L.heavy) : nullptr;
+    if (want_bin) OFR_CUDA(cudaMemsetAsync(w + L.counts, 0, L.offsets - L.counts, st));  // counts + misc
+
+    int rc;
+    if (g.C >= 8)
+        rc = launch_src<MODE, 8>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+    else
+        rc = launch_src<MODE, 1>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+    if (rc != OFR_OK || !want_bin) return rc;
+
+    scan_reduce_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, L.ncell);
+    OFR_LAUNCH_CHECK();
+    scan_top_kernel<<<1, 1024, 0, st>>>(blocksum, L.nblk);
+    OFR_LAUNCH_CHECK();
+    scan_apply_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, offsets, L.ncell);
+    OFR_LAUNCH_CHECK();
+    resample_fill_kernel<<<(unsigned)((L.npix + 255) / 256), 256, 0, st>>>(
+        key, rank, counts, offsets, entries, heavy, misc, L.npix, g.Hf * g.Wf, (g.Hin + 1) * (g.Win + 1));
+    OFR_LAUNCH_CHECK();
+    resample_sort_heavy_kernel<<<ofr::sm_count(), 512, 0, st>>>(heavy, misc, counts, offsets, entries);
+    OFR_LAUNCH_CHECK();
+    const long long ntgt = (long long)g.B * g.Hin * g.Win;
+    dim3 grid((unsigned)((ntgt + 127) / 128), (unsigned)((g.C + kTgtChunk - 1) / kTgtChunk));
+    resample_bwd_tgt_kernel<MODE><<<grid, 128, 0, st>>>(flow, gO, counts, offsets, entries, gI1, g);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+}  // namespace
+
+extern "C" int ofr_resample_fwd(const float* in1, const float* flow, float* out, int B, int C, int Hin, int Win,
+                                int Hf, int Wf, int mode, ofr_stream_t stream) {
+    if (!in1 || !flow || !out || !geom_ok(B, C, Hin, Win, Hf, Wf)) return OFR_EINVAL;
+    if ((mode == OFR_WARP_STN || mode == OFR_WARP_PWC) && (Hin != Hf || Win != Wf)) return OFR_EINVAL;
+    const WarpGeom g = make_geom(B, C, Hin, Win, Hf, Wf);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+        case OFR_WARP_FLOWNET2: return launch_fwd<OFR_WARP_FLOWNET2>(in1, flow, out, g, st);
+        case OFR_WARP_STN: return launch_fwd<OFR_WARP_STN>(in1, flow, out, g, st);
+        case OFR_WARP_PWC: return launch_fwd<OFR_WARP_PWC>(in1, flow, out, g, st);
+        case OFR_WARP_FLOWNET2_NEAREST: return launch_fwd<OFR_WARP_FLOWNET2_NEAREST>(in1, flow, out, g, st);
+        default: return OFR_EINVAL;
+    }
+}
+
+extern "C" size_t ofr_resample_bwd_workspace(int B, int C, int Hin, int Win, int Hf, int Wf, int mode) {
+    (void)mode;
+    if (!geom_ok(B, C, Hin, Win, Hf, Wf)) return 0;
+    return ws_layout(B, Hin, Win, Hf, Wf).total;
+}
+
+extern "C" int ofr_resample_bwd(const float* in1, const float* flow, const float* gO, float* gI1, float* gI2, int B,
+                                int C, int Hin, int Win, int Hf, int Wf, int mode, void* ws, size_t ws_bytes,
+                                ofr_stream_t stream) {
+    if (!in1 || !flow || !gO || !geom_ok(B, C, Hin, Win, Hf, Wf)) return OFR_EINVAL;
+    if (!gI1 && !gI2) return OFR_OK;
+    if ((mode == OFR_WARP_STN || mode == OFR_WARP_PWC) && (Hin != Hf || Win != Wf)) return OFR_EINVAL;
+    if (mode == OFR_WARP_FLOWNET2_NEAREST) return OFR_ENOTSUP;
+    if (gI1) {
+        if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < ws_layout(B, Hin, Win, Hf, Wf).total)
+            return OFR_EWORKSPACE;
+    }
+    const WarpGeom g = make_geom(B, C, Hin, Win, Hf, Wf);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+        case OFR_WARP_FLOWNET2: return run_bwd<OFR_WARP_FLOWNET2>(in1, flow, gO, gI1, gI2, g, ws, st);
+        case OFR_WARP_STN: return run_bwd<OFR_WARP_STN>(in1, flow, gO, gI1, gI2, g, ws, st);
+        case OFR_WARP_PWC: return run_bwd<OFR_WARP_PWC>(in1, flow, gO, gI1, gI2, g, ws, st);
+        default: return OFR_EINVAL;
+    }
+}

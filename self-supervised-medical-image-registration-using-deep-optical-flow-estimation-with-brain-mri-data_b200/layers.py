@@ -1,0 +1,236 @@
+"""The reference's custom-layer API, backed by the sm_100a kernels through the C ABI.
+
+Module classes keep the flownet2 names and constructor signatures the reference model files use
+(``flownet2/networks/FlowNetC.py:28,31``, ``flownet2/models.py:40,52``, ``PWC/models/PWCNet.py:69``):
+
+    Correlation(pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)(in1, in2)
+    Resample2d(kernel_size=1, bilinear=True)(in1, flow)
+    ChannelNorm(norm_deg=2)(in1)
+
+plus the two in-tree warps as functions (``stn_warp`` = ``models.py:256-268``, ``pwc_warp`` =
+``PWC/models/PWCNet.py:143-179``).  All are parameter-free, differentiable w.r.t. every tensor
+input, float32 / CUDA only.  There is no CPU path: a CPU tensor raises.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import WARP_FLOWNET2, WARP_FLOWNET2_NEAREST, WARP_PWC, WARP_STN
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _prep(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: ofr_b200 layers run on CUDA tensors only (got {t.device}); "
+                           "there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype} (wrap in tofp32()/tofp16() as the reference does)")
+    if t.dim() != 4:
+        raise ValueError(f"{name}: expected a 4-D NCHW tensor, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _workspace(nbytes, device):
+    """256-byte aligned scratch from the caching allocator (the library itself never allocates)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------ Correlation
+def correlation_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2):
+    d, ho, wo = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = _lib.lib().ofr_corr_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                                       ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo))
+    if rc != 0:
+        raise ValueError(f"Correlation: invalid geometry H={H} W={W} pad={pad_size} k={kernel_size} "
+                         f"md={max_displacement} s1={stride1} s2={stride2}")
+    return d.value, ho.value, wo.value
+
+
+class _CorrelationFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input1, input2, pad, k, md, s1, s2):
+        input1, input2 = _prep(input1, "Correlation input1"), _prep(input2, "Correlation input2")
+        if input1.shape != input2.shape:
+            raise ValueError(f"Correlation: input shapes differ {tuple(input1.shape)} vs {tuple(input2.shape)}")
+        B, C, H, W = input1.shape
+        D, Ho, Wo = correlation_out_shape(H, W, pad, k, md, s1, s2)
+        out = torch.empty(B, D * D, Ho, Wo, dtype=torch.float32, device=input1.device)
+        with torch.cuda.device(input1.device):
+            _lib.check(_lib.lib().ofr_corr_fwd(_ptr(input1), _ptr(input2), _ptr(out), B, C, H, W, pad, k, md, s1, s2,
+                                               _stream()), "ofr_corr_fwd")
+        ctx.save_for_backward(input1, input2)
+        ctx.geom = (pad, k, md, s1, s2)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        input1, input2 = ctx.saved_tensors
+        pad, k, md, s1, s2 = ctx.geom
+        B, C, H, W = input1.shape
+        grad_out = _prep(grad_out, "Correlation grad_output")
+        g1 = torch.empty_like(input1) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty_like(input2) if ctx.needs_input_grad[1] else None
+        if g1 is not None or g2 is not None:
+            with torch.cuda.device(input1.device):
+                _lib.check(_lib.lib().ofr_corr_bwd(_ptr(input1), _ptr(input2), _ptr(grad_out), _ptr(g1), _ptr(g2),
+                                                   B, C, H, W, pad, k, md, s1, s2, _stream()), "ofr_corr_bwd")
+        return g1, g2, None, None, None, None, None
+
+
+class Correlation(nn.Module):
+    """Cost volume.  Same constructor as flownet2's ``Correlation`` (defaults included);
+    ``corr_multiply`` is accepted and ignored, as upstream."""
+
+    def __init__(self, pad_size=0, kernel_size=0, max_displacement=0, stride1=1, stride2=2, corr_multiply=1):
+        super().__init__()
+        self.pad_size = pad_size
+        self.kernel_size = kernel_size
+        self.max_displacement = max_displacement
+        self.stride1 = stride1
+        self.stride2 = stride2
+        self.corr_multiply = corr_multiply
+
+    def forward(self, input1, input2):
+        return _CorrelationFn.apply(input1, input2, self.pad_size, self.kernel_size, self.max_displacement,
+                                    self.stride1, self.stride2)
+
+    def extra_repr(self):
+        return (f"pad_size={self.pad_size}, kernel_size={self.kernel_size}, max_displacement={self.max_displacement}, "
+                f"stride1={self.stride1}, stride2={self.stride2}")
+
+
+def spatial_correlation_sample(input1, input2, kernel_size=1, patch_size=1, stride=1, padding=0, dilation=1,
+                               dilation_patch=1):
+    """Alias of the ClementPinard sampler for the one configuration the reference calls
+    (``FlowNetS/util.py:58-72``): un-normalised products, output ``(B, patch, patch, H, W)``."""
+    if kernel_size != 1 or stride != 1 or padding != 0 or dilation != 1 or patch_size % 2 != 1:
+        raise NotImplementedError("spatial_correlation_sample: only kernel_size=1, stride=1, padding=0, dilation=1 "
+                                  "with an odd patch_size is provided (FlowNetS/util.py:58-66)")
+    r = (patch_size - 1) // 2
+    md = r * dilation_patch
+    out = _CorrelationFn.apply(input1, input2, md, 1, md, 1, dilation_patch)
+    B, _, H, W = out.shape
+    return out.view(B, patch_size, patch_size, H, W) * float(input1.size(1))
+
+
+# ------------------------------------------------------------------------------------------ warps
+class _WarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input1, flow, mode):
+        input1, flow = _prep(input1, "warp input1"), _prep(flow, "warp flow")
+        B, C, Hin, Win = input1.shape
+        Bf, two, Hf, Wf = flow.shape
+        if Bf != B or two != 2:
+            raise ValueError(f"warp: flow must be [B,2,H,W] with B={B}, got {tuple(flow.shape)}")
+        if mode in (WARP_STN, WARP_PWC) and (Hin, Win) != (Hf, Wf):
+            raise ValueError("warp: image and flow must have the same spatial size")
+        out = torch.empty(B, C, Hf, Wf, dtype=torch.float32, device=input1.device)
+        with torch.cuda.device(input1.device):
+            _lib.check(_lib.lib().ofr_resample_fwd(_ptr(input1), _ptr(flow), _ptr(out), B, C, Hin, Win, Hf, Wf, mode,
+                                                   _stream()), "ofr_resample_fwd")
+        ctx.save_for_backward(input1, flow)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        input1, flow = ctx.saved_tensors
+        mode = ctx.mode
+        B, C, Hin, Win = input1.shape
+        _, _, Hf, Wf = flow.shape
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if mode == WARP_FLOWNET2_NEAREST:
+            if need1:
+                raise NotImplementedError("Resample2d(bilinear=False): image gradient is not provided")
+            return None, (torch.zeros_like(flow) if need2 else None), None
+        grad_out = _prep(grad_out, "warp grad_output")
+        g1 = torch.empty_like(input1) if need1 else None
+        g2 = torch.empty_like(flow) if need2 else None
+        if g1 is None and g2 is None:
+            return None, None, None
+        with torch.cuda.device(input1.device):
+            ws, ws_bytes = None, 0
+            if g1 is not None:
+                ws_bytes = int(_lib.lib().ofr_resample_bwd_workspace(B, C, Hin, Win, Hf, Wf, mode))
+                ws = _workspace(ws_bytes, input1.device)
+            _lib.check(_lib.lib().ofr_resample_bwd(_ptr(input1), _ptr(flow), _ptr(grad_out), _ptr(g1), _ptr(g2),
+                                                   B, C, Hin, Win, Hf, Wf, mode, _ptr(ws), ws_bytes, _stream()),
+                       "ofr_resample_bwd")
+        return g1, g2, None
+
+
+class Resample2d(nn.Module):
+    """Bilinear backward warp in pixel units, border-clamped taps (flownet2 ``Resample2d``)."""
+
+    def __init__(self, kernel_size=1, bilinear=True):
+        super().__init__()
+        if kernel_size != 1:
+            raise NotImplementedError("Resample2d: only kernel_size=1 (the value every reference call site uses, "
+                                      "flownet2/models.py:52-88) is provided")
+        self.kernel_size = kernel_size
+        self.bilinear = bilinear
+
+    def forward(self, input1, input2):
+        return _WarpFn.apply(input1, input2, WARP_FLOWNET2 if self.bilinear else WARP_FLOWNET2_NEAREST)
+
+
+def stn_warp(flow, frame):
+    """``opticalFlowReg.stn(flow, frame)`` (models.py:256-268): resize ``frame`` to the flow's size
+    (bilinear, align_corners=True), then sample it at (p+flow)*(2/w,2/h)-1 with zeros padding."""
+    h, w = flow.shape[2:]
+    if frame.shape[2:] != (h, w):
+        frame = F.interpolate(frame, size=(h, w), mode="bilinear", align_corners=True)
+    return _WarpFn.apply(frame, flow, WARP_STN)
+
+
+def pwc_warp(x, flo):
+    """``PWCDCNet.warp(x, flo)`` (PWC/models/PWCNet.py:143-179) in one pass: sample, build the
+    ones-mask, threshold at 0.9999 and multiply, without materialising grid or mask."""
+    return _WarpFn.apply(x, flo, WARP_PWC)
+
+
+# ------------------------------------------------------------------------------------------ ChannelNorm
+class _ChannelNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input1):
+        input1 = _prep(input1, "ChannelNorm input1")
+        B, C, H, W = input1.shape
+        out = torch.empty(B, 1, H, W, dtype=torch.float32, device=input1.device)
+        with torch.cuda.device(input1.device):
+            _lib.check(_lib.lib().ofr_chnorm_fwd(_ptr(input1), _ptr(out), B, C, H, W, _stream()), "ofr_chnorm_fwd")
+        ctx.save_for_backward(input1, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        input1, out = ctx.saved_tensors
+        B, C, H, W = input1.shape
+        grad_out = _prep(grad_out, "ChannelNorm grad_output")
+        g = torch.empty_like(input1)
+        with torch.cuda.device(input1.device):
+            _lib.check(_lib.lib().ofr_chnorm_bwd(_ptr(input1), _ptr(out), _ptr(grad_out), _ptr(g), B, C, H, W,
+                                                 _stream()), "ofr_chnorm_bwd")
+        return g
+
+
+class ChannelNorm(nn.Module):
+    """Per-pixel L2 norm over channels (flownet2 ``ChannelNorm``; ``norm_deg`` is ignored upstream too)."""
+
+    def __init__(self, norm_deg=2):
+        super().__init__()
+        self.norm_deg = norm_deg
+
+    def forward(self, input1):
+        return _ChannelNormFn.apply(input1)

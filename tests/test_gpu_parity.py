@@ -1,0 +1,306 @@
+"""GPU parity: every kernel, through the C ABI (ctypes -> libofr_b200.so), against the CPU oracle.
+
+Tolerances are the north-star's: max abs error <= 1e-5 on correlation and warp outputs, <= 1e-4
+relative (to the gradient's max magnitude) on gradients.  The oracle runs in float64 on the CPU.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ofr():
+    import ofr_b200
+    assert torch.cuda.is_available()
+    ofr_b200._lib.lib()  # must load: no fallback
+    return ofr_b200
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def close(got, ref, atol=0.0, rtol=0.0, what=""):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = (got - ref).abs().max().item() if ref.numel() else 0.0
+    bound = atol + rtol * (ref.abs().max().item() if ref.numel() else 0.0)
+    assert err <= bound, f"{what}: max abs err {err:.3e} > bound {bound:.3e}"
+
+
+def run_pair(ref_fn, dev_fn, inputs, out_atol, grad_rtol, what, grad_atol=1e-7):
+    """Forward + backward of ref_fn on CPU/float64 and dev_fn on the GPU/float32 with a shared cotangent."""
+    cpu = [t.detach().double().requires_grad_(True) for t in inputs]
+    ref = ref_fn(*cpu)
+    go = torch.randn(ref.shape, generator=gen(99), dtype=torch.float64)
+    rg = torch.autograd.grad(ref, cpu, go, allow_unused=True)
+    dev = [t.detach().float().to(DEV).requires_grad_(True) for t in inputs]
+    out = dev_fn(*dev)
+    dg = torch.autograd.grad(out, dev, go.float().to(DEV), allow_unused=True)
+    close(out, ref, atol=out_atol, what=what + " fwd")
+    for i, (g, r) in enumerate(zip(dg, rg)):
+        if r is None:
+            continue
+        close(g, r, atol=grad_atol, rtol=grad_rtol, what=f"{what} grad[{i}]")
+    return out, dg
+
+
+# =============================================================================== ChannelNorm
+@pytest.mark.parametrize("shape", [(2, 1, 16, 16), (3, 2, 8, 12), (2, 3, 7, 9), (1, 5, 1, 1), (2, 2, 33, 5)])
+def test_channelnorm(ofr, shape):
+    x = torch.randn(*shape, generator=gen(1))
+    xd = x.to(DEV).requires_grad_(True)
+    out = ofr.ChannelNorm()(xd)
+    close(out, oracle.channelnorm(x.double()), atol=1e-6, what="chnorm fwd")
+    go = torch.randn(out.shape, generator=gen(2))
+    (g,) = torch.autograd.grad(out, xd, go.to(DEV))
+    ref = oracle.channelnorm_backward(x.double(), oracle.channelnorm(x.double()), go.double())
+    close(g, ref, atol=1e-7, rtol=1e-5, what="chnorm bwd")
+
+
+def test_channelnorm_zero_input_has_finite_gradient(ofr):
+    xd = torch.zeros(1, 2, 4, 4, device=DEV, requires_grad=True)
+    out = ofr.ChannelNorm()(xd)
+    (g,) = torch.autograd.grad(out.sum(), xd)
+    assert torch.equal(out, torch.zeros_like(out)) and torch.equal(g, torch.zeros_like(g))
+
+
+# =============================================================================== Correlation
+CORR_CASES = {
+    # tag: (B, C, H, W, pad, k, md, s1, s2)
+    "pwc_l6": (2, 196, 4, 4, 4, 1, 4, 1, 1),
+    "pwc_l5": (2, 128, 8, 8, 4, 1, 4, 1, 1),
+    "pwc_l4": (2, 96, 16, 16, 4, 1, 4, 1, 1),
+    "pwc_l3": (1, 64, 32, 32, 4, 1, 4, 1, 1),
+    "pwc_l2": (1, 32, 64, 64, 4, 1, 4, 1, 1),
+    "pwc_ragged": (2, 13, 12, 20, 4, 1, 4, 1, 1),      # C not a multiple of the chunk, H not of the tile
+    "pwc_wide": (1, 8, 6, 136, 4, 1, 4, 1, 1),          # several x tiles with a ragged last one
+    "flownetc": (1, 256, 32, 32, 20, 1, 20, 1, 2),
+    "flownetc_small": (2, 20, 12, 16, 20, 1, 20, 1, 2),
+    "generic_w_odd": (2, 5, 9, 11, 4, 1, 4, 1, 1),      # W % 4 != 0 -> generic kernels
+    "generic_k3": (1, 3, 9, 10, 3, 3, 2, 1, 1),
+    "generic_s1": (1, 4, 12, 12, 4, 1, 4, 2, 2),
+    "generic_pad_lt_md": (1, 4, 16, 16, 2, 1, 4, 1, 1),  # output smaller than input
+    "generic_pad_gt_md": (1, 3, 8, 8, 6, 1, 4, 1, 2),    # output larger than input
+    "generic_s2_3": (1, 6, 12, 12, 6, 1, 6, 1, 3),
+}
+
+
+@pytest.mark.parametrize("tag", list(CORR_CASES))
+def test_correlation_fwd_bwd(ofr, tag):
+    B, C, H, W, pad, k, md, s1, s2 = CORR_CASES[tag]
+    f1 = torch.randn(B, C, H, W, generator=gen(3))
+    f2 = torch.randn(B, C, H, W, generator=gen(4))
+    run_pair(lambda a, b: oracle.correlation(a, b, pad, k, md, s1, s2),
+             lambda a, b: ofr.Correlation(pad, k, md, s1, s2, 1)(a, b),
+             [f1, f2], out_atol=1e-5, grad_rtol=1e-4, what=f"corr[{tag}]")
+
+
+@pytest.mark.parametrize("tag", ["pwc", "fnc", "k3", "s1"])
+def test_correlation_golden(ofr, golden, tag):
+    g = golden("corr")
+    pad, k, md, s1, s2 = (int(v) for v in g[f"{tag}_params"])
+    out = ofr.Correlation(pad, k, md, s1, s2, 1)(torch.from_numpy(g[f"{tag}_f1"]).to(DEV),
+                                                 torch.from_numpy(g[f"{tag}_f2"]).to(DEV))
+    close(out, torch.from_numpy(g[f"{tag}_out"]), atol=1e-5, what=f"corr golden {tag}")
+
+
+def test_correlation_one_hot(ofr):
+    H = W = 16
+    for md, s2 in [(4, 1), (20, 2)]:
+        r, D = md // s2, 2 * (md // s2) + 1
+        f1 = torch.zeros(1, 4, H, W)
+        f2 = torch.zeros(1, 4, H, W)
+        y0, x0, tj, ti = 7, 8, -2, 3
+        f1[0, 2, y0, x0] = 2.0
+        f2[0, 2, y0 + s2 * tj, x0 + s2 * ti] = 3.0
+        out = ofr.Correlation(md, 1, md, 1, s2, 1)(f1.to(DEV), f2.to(DEV)).cpu()
+        nz = out.nonzero()
+        assert nz.shape[0] == 1 and tuple(nz[0].tolist()) == (0, (tj + r) * D + (ti + r), y0, x0)
+        assert abs(out[tuple(nz[0].tolist())].item() - 6.0 / 4) < 1e-7
+
+
+def test_correlation_is_reproducible_and_skips_unneeded_grads(ofr):
+    f1 = torch.randn(2, 32, 16, 16, generator=gen(5)).to(DEV).requires_grad_(True)
+    f2 = torch.randn(2, 32, 16, 16, generator=gen(6)).to(DEV)
+    corr = ofr.Correlation(4, 1, 4, 1, 1, 1)
+    o1, o2 = corr(f1, f2), corr(f1, f2)
+    assert torch.equal(o1, o2)
+    (g,) = torch.autograd.grad(o1.sum(), f1)
+    (g2,) = torch.autograd.grad(o2.sum(), f1)
+    assert torch.equal(g, g2)
+
+
+def test_spatial_correlation_sample_alias(ofr):
+    # FlowNetS/util.py:58-72: patch 21, dilation_patch 2, then /C  ==  Correlation(20,1,20,1,2,1)
+    a = torch.randn(1, 6, 12, 12, generator=gen(7)).to(DEV)
+    b = torch.randn(1, 6, 12, 12, generator=gen(8)).to(DEV)
+    s = ofr.spatial_correlation_sample(a, b, kernel_size=1, patch_size=21, stride=1, padding=0, dilation_patch=2)
+    assert s.shape == (1, 21, 21, 12, 12)
+    close(s.view(1, 441, 12, 12) / 6, ofr.Correlation(20, 1, 20, 1, 2, 1)(a, b), atol=1e-6, what="scs alias")
+
+
+# =============================================================================== warps
+WARP_SHAPES = [(2, 3, 16, 16), (1, 1, 9, 13), (2, 17, 8, 12), (1, 5, 32, 20)]
+
+
+@pytest.mark.parametrize("shape", WARP_SHAPES)
+@pytest.mark.parametrize("mode", ["resample2d", "stn", "pwc"])
+def test_warp_fwd_bwd(ofr, mode, shape):
+    B, C, H, W = shape
+    img = torch.randn(B, C, H, W, generator=gen(10))
+    flow = torch.randn(B, 2, H, W, generator=gen(11)) * 3.0
+    fns = {
+        "resample2d": (lambda i, f: oracle.resample2d(i, f), lambda i, f: ofr.Resample2d()(i, f)),
+        "stn": (lambda i, f: oracle.stn_warp(f, i), lambda i, f: ofr.stn_warp(f, i)),
+        "pwc": (lambda i, f: oracle.pwc_warp(i, f), lambda i, f: ofr.pwc_warp(i, f)),
+    }
+    run_pair(fns[mode][0], fns[mode][1], [img, flow], out_atol=1e-5, grad_rtol=1e-4, what=f"{mode}{shape}",
+             grad_atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_resample2d_golden(ofr, golden, tag):
+    g = golden("resample")
+    out = ofr.Resample2d()(torch.from_numpy(g[f"{tag}_in1"]).to(DEV), torch.from_numpy(g[f"{tag}_flow"]).to(DEV))
+    close(out, torch.from_numpy(g[f"{tag}_out"]), atol=1e-5, what="resample golden")
+
+
+def test_warps_vs_reference_golden(ofr, golden):
+    g = golden("warps")
+    frame = torch.from_numpy(g["stn_frame"]).to(DEV)
+    for tag in "abc":
+        out = ofr.stn_warp(torch.from_numpy(g[f"stn_flow_{tag}"]).to(DEV), frame)
+        close(out, torch.from_numpy(g[f"stn_out_{tag}"]), atol=1e-5, what=f"stn golden {tag}")
+    for tag in "ab":
+        out = ofr.pwc_warp(torch.from_numpy(g[f"pwc_x_{tag}"]).to(DEV), torch.from_numpy(g[f"pwc_flow_{tag}"]).to(DEV))
+        close(out, torch.from_numpy(g[f"pwc_out_{tag}"]), atol=1e-5, what=f"pwc golden {tag}")
+    out = ofr.pwc_warp(torch.from_numpy(g["pwc_zero_x"]).to(DEV), torch.zeros(1, 2, 8, 8, device=DEV))
+    close(out, torch.from_numpy(g["pwc_zero_out"]), atol=1e-6, what="pwc zero flow")
+    assert int((out == 0).sum()) == 28
+
+
+def test_resample2d_identity_shift_and_sizes(ofr):
+    img = torch.randn(2, 3, 12, 16, generator=gen(12)).to(DEV)
+    z = torch.zeros(2, 2, 12, 16, device=DEV)
+    assert torch.equal(ofr.Resample2d()(img, z), img)
+    fl = z.clone()
+    fl[:, 0] = 3.0
+    fl[:, 1] = -2.0
+    out = ofr.Resample2d()(img, fl)
+    assert torch.equal(out[:, :, 2:, :-3], img[:, :, :-2, 3:])
+    assert torch.equal(out[:, :, 2:, -1], img[:, :, :-2, -1])  # clamped border
+    # flow smaller than the image: output takes the flow's size, taps clamp to the image
+    fl2 = torch.randn(2, 2, 6, 8, generator=gen(13)) * 4
+    ref = oracle.resample2d(img.cpu().double(), fl2.double())
+    close(ofr.Resample2d()(img, fl2.to(DEV)), ref, atol=1e-5, what="resample Hin != Hf")
+    # nearest mode
+    refn = oracle.resample2d(img.cpu().double(), fl2.double(), bilinear=False)
+    close(ofr.Resample2d(bilinear=False)(img, fl2.to(DEV)), refn, atol=0, what="resample nearest")
+
+
+@pytest.mark.parametrize("mode", ["resample2d", "pwc", "stn"])
+def test_warp_backward_is_bitwise_deterministic(ofr, mode):
+    """North-star rule 3: the adjoint scatter must not depend on execution order."""
+    B, C, H, W = 2, 24, 32, 32
+    img = torch.randn(B, C, H, W, generator=gen(14)).to(DEV).requires_grad_(True)
+    flow = (torch.randn(B, 2, H, W, generator=gen(15)) * 4).to(DEV).requires_grad_(True)
+    go = torch.randn(B, C, H, W, generator=gen(16)).to(DEV)
+    fn = {"resample2d": lambda: ofr.Resample2d()(img, flow), "pwc": lambda: ofr.pwc_warp(img, flow),
+          "stn": lambda: ofr.stn_warp(flow, img)}[mode]
+    first = torch.autograd.grad(fn(), (img, flow), go)
+    for _ in range(4):
+        again = torch.autograd.grad(fn(), (img, flow), go)
+        assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1])
+
+
+@pytest.mark.parametrize("kind", ["collapse_point", "collapse_row", "far_outside", "constant_shift"])
+def test_warp_backward_degenerate_flows(ofr, kind):
+    """Crowded cells (many sources on one target) take the pre-sorted path; results stay exact and reproducible."""
+    B, C, H, W = 1, 9, 24, 40
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    flow = torch.zeros(B, 2, H, W)
+    if kind == "collapse_point":      # every pixel samples around (5.3, 7.6)
+        flow[:, 0], flow[:, 1] = 5.3 - xs, 7.6 - ys
+    elif kind == "collapse_row":      # every pixel of a row samples column 3.5
+        flow[:, 0] = 3.5 - xs
+    elif kind == "far_outside":       # everything clamps to the bottom-right corner / falls outside
+        flow[:] = 1000.0
+    else:
+        flow[:, 0], flow[:, 1] = 2.25, -1.5
+    img = torch.randn(B, C, H, W, generator=gen(17))
+    for ref_fn, dev_fn, name in [(lambda i, f: oracle.resample2d(i, f), lambda i, f: ofr.Resample2d()(i, f), "resample2d"),
+                                 (lambda i, f: oracle.pwc_warp(i, f), lambda i, f: ofr.pwc_warp(i, f), "pwc")]:
+        cpu = [img.double().requires_grad_(True), flow.double().requires_grad_(True)]
+        ref = ref_fn(*cpu)
+        go = torch.randn(ref.shape, generator=gen(18), dtype=torch.float64)
+        (rg,) = torch.autograd.grad(ref, cpu[:1], go)
+        dev = [img.to(DEV).requires_grad_(True), flow.to(DEV)]
+        g1 = torch.autograd.grad(dev_fn(*dev), dev[:1], go.float().to(DEV))[0]
+        g2 = torch.autograd.grad(dev_fn(*dev), dev[:1], go.float().to(DEV))[0]
+        assert torch.equal(g1, g2)
+        close(g1, rg, atol=1e-5, rtol=2e-4, what=f"{name} {kind} dImg")
+
+
+# =============================================================================== loss
+def test_loss_vs_reference_golden(ofr, golden):
+    g = golden("loss")
+    fixed = torch.from_numpy(g["fixed"]).to(DEV)
+    flows = [torch.from_numpy(g[f"flow{i}"]).to(DEV).requires_grad_(True) for i in range(4)]
+    warped = [torch.from_numpy(g[f"warped{i}"]).to(DEV).requires_grad_(True) for i in range(4)]
+    res = ofr.OFEloss(flows, warped, fixed)
+    assert all(t.dtype == torch.float64 and t.dim() == 0 for t in res)
+    np.testing.assert_allclose([t.item() for t in res], g["ofe"], rtol=2e-6)
+    grads = torch.autograd.grad(res[3], flows + warped)
+    for i in range(4):
+        close(grads[i], torch.from_numpy(g[f"gflow{i}"]), atol=1e-6, rtol=1e-4, what=f"loss gflow{i}")
+        close(grads[4 + i], torch.from_numpy(g[f"gwarped{i}"]), atol=1e-6, rtol=1e-4, what=f"loss gwarped{i}")
+    res = ofr.OFEloss(flows[:2], warped[:2], fixed, lamb_da=0.25, gamma=10.0, zeta=3.0)
+    np.testing.assert_allclose([t.item() for t in res], g["ofe_alt"], rtol=2e-6)
+    for i in range(4):
+        np.testing.assert_allclose(ofr.photometric_loss(fixed, warped[i].detach()).item(), g[f"photo{i}"], rtol=2e-6)
+        np.testing.assert_allclose(ofr.correlation_loss(fixed, warped[i].detach()).item(), g[f"ncc{i}"], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(ofr.smoothness_loss(flows[i].detach()).item(), g[f"smooth{i}"], rtol=2e-6)
+
+
+def test_loss_individual_term_gradients(ofr):
+    fixed = torch.rand(2, 1, 64, 64, generator=gen(20))
+    sizes = [64, 32, 16, 8, 4]
+    flows = [torch.randn(2, 2, s, s, generator=gen(21 + s)) for s in sizes]
+    warps = [torch.rand(2, 1, s, s, generator=gen(31 + s)) for s in sizes]
+    for k in range(4):  # backward from each of the four returned terms
+        cf = [f.clone().requires_grad_(True) for f in flows]
+        cw = [w.clone().requires_grad_(True) for w in warps]
+        ref = oracle.ofe_loss(cf, cw, fixed)
+        rg = torch.autograd.grad(ref[k], cf + cw, allow_unused=True)
+        df = [f.to(DEV).requires_grad_(True) for f in flows]
+        dw = [w.to(DEV).requires_grad_(True) for w in warps]
+        got = ofr.OFEloss(df, dw, fixed.to(DEV))
+        np.testing.assert_allclose(got[k].item(), ref[k].item(), rtol=2e-6)
+        dg = torch.autograd.grad(got[k], df + dw, allow_unused=True)
+        for i, (a, b) in enumerate(zip(dg, rg)):
+            if b is None:
+                assert a is None or float(a.abs().max()) == 0.0
+            else:
+                close(a, b, atol=1e-6, rtol=1e-4, what=f"term{k} grad{i}")
+
+
+def test_loss_degenerate_and_reproducible(ofr, golden):
+    g = golden("loss")
+    fixed = torch.from_numpy(g["fixed"]).to(DEV)
+    const = torch.full((3, 1, 16, 16), 0.5, device=DEV)
+    assert ofr.correlation_loss(fixed, const).item() == float(g["ncc_const"]) == 0.0   # loss.py:59-60
+    z = ofr.smoothness_loss(torch.zeros(3, 2, 8, 8, device=DEV)).item()
+    np.testing.assert_allclose(z, float(g["smooth_zero"]), rtol=1e-6)
+    flows = [torch.randn(3, 2, 32, 32, generator=gen(40)).to(DEV)]
+    warps = [torch.rand(3, 1, 32, 32, generator=gen(41)).to(DEV)]
+    a = ofr.OFEloss(flows, warps, fixed)
+    b = ofr.OFEloss(flows, warps, fixed)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
