@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .profiling import region
 from ._lib import WARP_FLOWNET2, WARP_FLOWNET2_NEAREST, WARP_PWC, WARP_STN
 
 
@@ -67,7 +68,8 @@ class _CorrelationFn(torch.autograd.Function):
         B, C, H, W = input1.shape
         D, Ho, Wo = correlation_out_shape(H, W, pad, k, md, s1, s2)
         out = torch.empty(B, D * D, Ho, Wo, dtype=torch.float32, device=input1.device)
-        with torch.cuda.device(input1.device):
+        nbytes = 4 * (2 * B * C * H * W + B * D * D * Ho * Wo)
+        with torch.cuda.device(input1.device), region(f"corr_fwd C{C} {H}x{W} D{D}", nbytes, 2 * B * D * D * C * Ho * Wo):
             _lib.check(_lib.lib().ofr_corr_fwd(_ptr(input1), _ptr(input2), _ptr(out), B, C, H, W, pad, k, md, s1, s2,
                                                _stream()), "ofr_corr_fwd")
         ctx.save_for_backward(input1, input2)
@@ -83,7 +85,11 @@ class _CorrelationFn(torch.autograd.Function):
         g1 = torch.empty_like(input1) if ctx.needs_input_grad[0] else None
         g2 = torch.empty_like(input2) if ctx.needs_input_grad[1] else None
         if g1 is not None or g2 is not None:
-            with torch.cuda.device(input1.device):
+            ng = (g1 is not None) + (g2 is not None)
+            Dd = grad_out.shape[1]
+            nbytes = 4 * (2 * B * C * H * W + grad_out.numel() + ng * B * C * H * W)
+            with torch.cuda.device(input1.device), region(f"corr_bwd C{C} {H}x{W} D2={Dd} g{ng}", nbytes,
+                                                          2 * ng * grad_out.numel() * C):
                 _lib.check(_lib.lib().ofr_corr_bwd(_ptr(input1), _ptr(input2), _ptr(grad_out), _ptr(g1), _ptr(g2),
                                                    B, C, H, W, pad, k, md, s1, s2, _stream()), "ofr_corr_bwd")
         return g1, g2, None, None, None, None, None
@@ -137,7 +143,7 @@ class _WarpFn(torch.autograd.Function):
         if mode in (WARP_STN, WARP_PWC) and (Hin, Win) != (Hf, Wf):
             raise ValueError("warp: image and flow must have the same spatial size")
         out = torch.empty(B, C, Hf, Wf, dtype=torch.float32, device=input1.device)
-        with torch.cuda.device(input1.device):
+        with torch.cuda.device(input1.device), region(f"warp_fwd m{mode} C{C} {Hf}x{Wf}", 4 * B * Hf * Wf * (2 * C + 2)):
             _lib.check(_lib.lib().ofr_resample_fwd(_ptr(input1), _ptr(flow), _ptr(out), B, C, Hin, Win, Hf, Wf, mode,
                                                    _stream()), "ofr_resample_fwd")
         ctx.save_for_backward(input1, flow)
@@ -160,7 +166,9 @@ class _WarpFn(torch.autograd.Function):
         g2 = torch.empty_like(flow) if need2 else None
         if g1 is None and g2 is None:
             return None, None, None
-        with torch.cuda.device(input1.device):
+        nbytes = 4 * B * Hf * Wf * (2 * C + 2 + (C if g1 is not None else 0) + (2 if g2 is not None else 0))
+        with torch.cuda.device(input1.device), region(
+                f"warp_bwd m{mode} C{C} {Hf}x{Wf} gI1={int(g1 is not None)} gI2={int(g2 is not None)}", nbytes):
             ws, ws_bytes = None, 0
             if g1 is not None:
                 ws_bytes = int(_lib.lib().ofr_resample_bwd_workspace(B, C, Hin, Win, Hf, Wf, mode))
@@ -208,7 +216,7 @@ class _ChannelNormFn(torch.autograd.Function):
         input1 = _prep(input1, "ChannelNorm input1")
         B, C, H, W = input1.shape
         out = torch.empty(B, 1, H, W, dtype=torch.float32, device=input1.device)
-        with torch.cuda.device(input1.device):
+        with torch.cuda.device(input1.device), region(f"chnorm_fwd C{C} {H}x{W}", 4 * B * H * W * (C + 1)):
             _lib.check(_lib.lib().ofr_chnorm_fwd(_ptr(input1), _ptr(out), B, C, H, W, _stream()), "ofr_chnorm_fwd")
         ctx.save_for_backward(input1, out)
         return out
@@ -219,7 +227,7 @@ class _ChannelNormFn(torch.autograd.Function):
         B, C, H, W = input1.shape
         grad_out = _prep(grad_out, "ChannelNorm grad_output")
         g = torch.empty_like(input1)
-        with torch.cuda.device(input1.device):
+        with torch.cuda.device(input1.device), region(f"chnorm_bwd C{C} {H}x{W}", 4 * B * H * W * (2 * C + 2)):
             _lib.check(_lib.lib().ofr_chnorm_bwd(_ptr(input1), _ptr(out), _ptr(grad_out), _ptr(g), B, C, H, W,
                                                  _stream()), "ofr_chnorm_bwd")
         return g

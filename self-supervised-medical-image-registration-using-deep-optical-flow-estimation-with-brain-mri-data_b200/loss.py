@@ -12,6 +12,7 @@ import torch
 
 from . import _lib
 from .layers import _prep, _ptr, _stream, _workspace
+from .profiling import region
 
 
 def _pack_scales(flows, warpeds, g_warped=None, g_flow=None):
@@ -45,7 +46,8 @@ class _OFELossFn(torch.autograd.Function):
         dev = fixed.device
         out4 = torch.empty(4, dtype=torch.float64, device=dev)
         state = torch.empty(n * _lib.LOSS_STATE_DOUBLES, dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        px = sum(int(w.shape[2]) * int(w.shape[3]) for w in warpeds)
+        with torch.cuda.device(dev), region(f"loss_fwd n{n} {Hs}x{Ws}", 4 * B * (3 * px + Hs * Ws)):
             ws_bytes = int(_lib.lib().ofr_loss_workspace(n))
             ws = _workspace(ws_bytes, dev)
             scales = _pack_scales(flows, warpeds)
@@ -69,7 +71,8 @@ class _OFELossFn(torch.autograd.Function):
         need = ctx.needs_input_grad[5:]
         g_flow = [torch.empty_like(flows[i]) if need[i] else None for i in range(n)]
         g_warped = [torch.empty_like(warpeds[i]) if need[n + i] else None for i in range(n)]
-        with torch.cuda.device(dev):
+        px = sum(int(w.shape[2]) * int(w.shape[3]) for w in warpeds)
+        with torch.cuda.device(dev), region(f"loss_bwd n{n} {Hs}x{Ws}", 4 * B * (6 * px + Hs * Ws)):
             scales = _pack_scales(flows, warpeds, g_warped, g_flow)
             _lib.check(_lib.lib().ofr_loss_bwd(_ptr(fixed), B, Hs, Ws, scales, n, lamb_da, gamma, zeta,
                                                _ptr(grad4), _ptr(state), _stream()), "ofr_loss_bwd")

@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmark of the C-ABI entry points at the shapes of the reference's models.
+
+    python tools/opbench.py [--only REGEX] [--iters N] [--json out.json] [--size 512] [--batch 24]
+
+Every case calls libofr_b200.so directly (no autograd), brackets each call with CUDA events on the
+launching stream, and flushes the L2 (writes a 256 MB buffer) between iterations.  Reports the median
+duration, algorithmic GB/s (SURVEY.md 8d formulas), fraction of the measured HBM peak and fp32 TFLOP/s.
+Used for development and for ncu captures (`ncu -k regex:... python tools/opbench.py --only ... --iters 3`).
+"""
+import argparse
+import ctypes
+import json
+import os
+import re
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import ofr_b200  # noqa: E402
+from ofr_b200 import _lib  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def cases(B, S):
+    L = _lib.lib()
+    out = []
+
+    def corr(tag, C, h, pad, md, s2):
+        f1 = torch.randn(B, C, h, h, device=DEV)
+        f2 = torch.randn(B, C, h, h, device=DEV)
+        D = 2 * (md // s2) + 1
+        o = torch.empty(B, D * D, h, h, device=DEV)
+        go = torch.randn_like(o)
+        g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
+        flops = 2 * B * D * D * C * h * h
+        out.append((f"corr_fwd {tag} C{C} {h}x{h}", 4 * (2 * f1.numel() + o.numel()), flops,
+                    lambda: L.ofr_corr_fwd(P(f1), P(f2), P(o), B, C, h, h, pad, 1, md, 1, s2, stream())))
+        out.append((f"corr_bwd {tag} C{C} {h}x{h}", 4 * (4 * f1.numel() + o.numel()), 2 * flops,
+                    lambda: L.ofr_corr_bwd(P(f1), P(f2), P(go), P(g1), P(g2), B, C, h, h, pad, 1, md, 1, s2, stream())))
+
+    def warp(tag, C, h, mode, want1, sigma):
+        x = torch.randn(B, C, h, h, device=DEV)
+        fl = torch.randn(B, 2, h, h, device=DEV) * sigma
+        o = torch.empty_like(x)
+        go = torch.randn_like(x)
+        g1 = torch.empty_like(x) if want1 else None
+        g2 = torch.empty_like(fl)
+        wsb = int(L.ofr_resample_bwd_workspace(B, C, h, h, h, h, mode)) if want1 else 0
+        ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=DEV)
+        out.append((f"warp_fwd {tag} m{mode} C{C} {h}x{h}", 4 * B * h * h * (2 * C + 2), 0,
+                    lambda: L.ofr_resample_fwd(P(x), P(fl), P(o), B, C, h, h, h, h, mode, stream())))
+        out.append((f"warp_bwd {tag} m{mode} C{C} {h}x{h} gI1={int(want1)}",
+                    4 * B * h * h * (2 * C + 2 + (C if want1 else 0) + 2), 0,
+                    lambda: L.ofr_resample_bwd(P(x), P(fl), P(go), P(g1), P(g2), B, C, h, h, h, h, mode, P(ws), wsb,
+                                               stream())))
+
+    def chnorm(C, h):
+        x = torch.randn(B, C, h, h, device=DEV)
+        o = torch.empty(B, 1, h, h, device=DEV)
+        go = torch.randn_like(o)
+        g = torch.empty_like(x)
+        out.append((f"chnorm_fwd C{C} {h}x{h}", 4 * B * h * h * (C + 1), 0,
+                    lambda: L.ofr_chnorm_fwd(P(x), P(o), B, C, h, h, stream())))
+        out.append((f"chnorm_bwd C{C} {h}x{h}", 4 * B * h * h * (2 * C + 2), 0,
+                    lambda: L.ofr_chnorm_bwd(P(x), P(o), P(go), P(g), B, C, h, h, stream())))
+
+    def loss(n):
+        fixed = torch.rand(B, 1, S, S, device=DEV)
+        sizes = [S >> i for i in range(n)]
+        flows = [torch.randn(B, 2, s, s, device=DEV) for s in sizes]
+        warps = [torch.rand(B, 1, s, s, device=DEV) for s in sizes]
+        gfl = [torch.empty_like(f) for f in flows]
+        gwp = [torch.empty_like(w) for w in warps]
+        arr = (_lib.LossScale * n)()
+        for i in range(n):
+            arr[i].warped, arr[i].flow = warps[i].data_ptr(), flows[i].data_ptr()
+            arr[i].g_warped, arr[i].g_flow = gwp[i].data_ptr(), gfl[i].data_ptr()
+            arr[i].h = arr[i].w = sizes[i]
+        out4 = torch.empty(4, dtype=torch.float64, device=DEV)
+        state = torch.empty(n * 16, dtype=torch.float64, device=DEV)
+        g4 = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=DEV)
+        wsb = int(L.ofr_loss_workspace(n))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        px = sum(s * s for s in sizes)
+        keep = (fixed, flows, warps, gfl, gwp, arr)
+        out.append((f"loss_fwd n{n} {S}x{S}", 4 * B * (3 * px + S * S), 0,
+                    lambda: (keep, L.ofr_loss_fwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(out4), P(state), P(ws),
+                                                  wsb, stream()))[1]))
+        out.append((f"loss_bwd n{n} {S}x{S}", 4 * B * (6 * px + S * S), 0,
+                    lambda: (keep, L.ofr_loss_bwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(g4), P(state),
+                                                  stream()))[1]))
+
+    # PWC-Net pyramid (PWCNet.py:200-259): levels 2..6
+    for lvl, C in [(2, 32), (3, 64), (4, 96), (5, 128), (6, 196)]:
+        corr(f"pwc_l{lvl}", C, S >> lvl, 4, 4, 1)
+    for lvl, C in [(2, 32), (3, 64), (4, 96), (5, 128)]:
+        warp(f"pwc_l{lvl}", C, S >> lvl, _lib.WARP_PWC, True, 2.0)
+    # FlowNetC correlation (FlowNetC.py:31,88) at 1/8 resolution
+    corr("flownetc", 256, S >> 3, 20, 20, 2)
+    # FlowNet2 full-resolution ops (flownet2/models.py:139-180) and the stn warp of the loss (models.py:256-268)
+    warp("flownet2", 1, S, _lib.WARP_FLOWNET2, False, 4.0)
+    warp("stn", 1, S, _lib.WARP_STN, False, 4.0)
+    chnorm(1, S)
+    chnorm(2, S)
+    loss(7)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=".*")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=24)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    peak = 6556.2
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk))["hbm_gbs"])
+    torch.manual_seed(6)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    rows = []
+    for name, nbytes, flops, fn in cases(args.batch, args.size):
+        if not re.search(args.only, name):
+            continue
+        for _ in range(3):
+            rc = fn()
+            assert rc == 0, (name, rc)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.iters):
+            if not args.no_flush:
+                flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = statistics.median(ts)
+        gbs = nbytes / us / 1e3
+        row = dict(kernel=name, us=round(us, 2), min_us=round(min(ts), 2), MB=round(nbytes / 1e6, 2),
+                   gbs=round(gbs, 1), hbm_frac=round(gbs / peak, 4), tflops=round(flops / us / 1e6, 2))
+        rows.append(row)
+        print(f"{name:44s} {us:9.1f} us  {nbytes/1e6:8.1f} MB {gbs:8.1f} GB/s  {100*gbs/peak:5.1f}% HBM  "
+              f"{row['tflops']:6.2f} TFLOP/s", flush=True)
+    if args.json:
+        json.dump(dict(peak_hbm_gbs=peak, batch=args.batch, size=args.size, rows=rows), open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
