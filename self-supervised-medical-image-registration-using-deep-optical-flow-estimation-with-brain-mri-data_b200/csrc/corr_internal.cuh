@@ -1,0 +1,20 @@
+// Shared between correlation.cu (generic + register-tiled kernels, ABI entry points) and correlation_tma.cu.
+#pragma once
+#include "ofr_common.cuh"
+
+namespace ofr {
+
+struct CorrGeom {
+    int B, C, H, W;
+    int pad, k, md, s1, s2;
+    int r, D, Hout, Wout;
+    float scale;  // 1 / (k*k*C)
+};
+
+// TMA-staged kernels for Correlation(4,1,4,1,1).  Return OFR_ENOTSUP (nothing launched) when the geometry or the
+// pointer alignment does not fit; the caller then falls back to the generic kernels.
+int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st);
+int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
+                 cudaStream_t st);
+
+}  // namespace ofr

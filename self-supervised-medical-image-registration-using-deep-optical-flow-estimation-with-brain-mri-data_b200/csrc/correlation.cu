@@ -14,16 +14,11 @@
 //    channel sum is a fixed-order loop -> bitwise reproducible.
 //  * generic (any k, s1, s2, pad): direct kernels, one thread per output element.  Correct for every
 //    parameter set the Python module accepts; only reached by configurations the reference never uses.
-#include "ofr_common.cuh"
+#include "corr_internal.cuh"
 
 namespace {
 
-struct CorrGeom {
-    int B, C, H, W;
-    int pad, k, md, s1, s2;
-    int r, D, Hout, Wout;
-    float scale;  // 1 / (k*k*C)
-};
+using ofr::CorrGeom;
 
 bool make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int k, int md, int s1, int s2) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || k < 1 || (k & 1) == 0 || md < 0 || s1 < 1 || s2 < 1)
@@ -331,7 +326,11 @@ extern "C" int ofr_corr_fwd(const float* f1, const float* f2, float* out, int B,
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec_ok = k == 1 && s1 == 1 && (W % 4 == 0) && ((md - pad) % 4 == 0) && ((g.r * s2) % 4 == 0) &&
                         ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(out) && (g.Wout % 4 == 0);
-    if (vec_ok && s2 == 1 && g.r == 4) {  // PWC-Net: Correlation(4,1,4,1,1)  (PWCNet.py:69)
+    {  // PWC-Net: Correlation(4,1,4,1,1) (PWCNet.py:69) -> TMA-staged kernels
+        const int rc = ofr::corr_fwd_tma(f1, f2, out, g, st);
+        if (rc != OFR_ENOTSUP) return rc;
+    }
+    if (vec_ok && s2 == 1 && g.r == 4) {  // same geometry without TMA (misaligned bases): register-tiled kernel
         if (g.Wout >= 64) return launch_tiled<1, 4, 8, 4, 8, 9, 8>(f1, f2, out, g, st);   // 4 x 64 tile
         if (g.Wout >= 32) return launch_tiled<1, 4, 8, 4, 4, 9, 8>(f1, f2, out, g, st);   // 4 x 32 tile
         if (g.Wout >= 16) return launch_tiled<1, 4, 8, 4, 2, 9, 8>(f1, f2, out, g, st);   // 4 x 16 tile
@@ -351,6 +350,11 @@ extern "C" int ofr_corr_bwd(const float* f1, const float* f2, const float* gO, f
     CorrGeom g;
     if (!f1 || !f2 || !gO || !make_geom(g, B, C, H, W, pad, k, md, s1, s2)) return OFR_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!gI1 && !gI2) return OFR_OK;
+    {
+        const int rc = ofr::corr_bwd_tma(f1, f2, gO, gI1, gI2, g, st);
+        if (rc != OFR_ENOTSUP) return rc;
+    }
     const long long total = (long long)B * C * H * W;
     if (gI1) {
         corr_bwd_generic_kernel<false><<<ofr::grid_for(total, 256, 8), 256, 0, st>>>(f2, gO, gI1, g);

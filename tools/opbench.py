@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--json", default=None)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
     peak = 6556.2
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -139,7 +140,7 @@ def main():
     for name, nbytes, flops, fn in cases(args.batch, args.size):
         if not re.search(args.only, name):
             continue
-        for _ in range(3):
+        for _ in range(args.warmup):
             rc = fn()
             assert rc == 0, (name, rc)
         torch.cuda.synchronize()
