@@ -12,6 +12,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kCtasPerSm = 8;
+// every launch covers the whole tensor with one vector per thread (no grid-stride tail): the block scheduler keeps
+// 8 x 256 threads resident per SM, each with its loads in flight
 
 template <int VEC>
 struct Pix;
@@ -98,10 +100,10 @@ extern "C" int ofr_chnorm_fwd(const float* x, float* out, int B, int C, int H, i
     cudaStream_t st = (cudaStream_t)stream;
     if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out)) {
         const long long n = (long long)B * hw / 4;
-        chnorm_fwd_kernel<4><<<ofr::grid_for(n, kThreads, kCtasPerSm), kThreads, 0, st>>>(x, out, C, hw, n);
+        chnorm_fwd_kernel<4><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_fwd_kernel<1><<<ofr::grid_for(n, kThreads, kCtasPerSm), kThreads, 0, st>>>(x, out, C, hw, n);
+        chnorm_fwd_kernel<1><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;
@@ -114,10 +116,10 @@ extern "C" int ofr_chnorm_bwd(const float* x, const float* out, const float* gO,
     cudaStream_t st = (cudaStream_t)stream;
     if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && ofr::aligned16(gO) && ofr::aligned16(gI)) {
         const long long n = (long long)B * hw / 4;
-        chnorm_bwd_kernel<4><<<ofr::grid_for(n, kThreads, kCtasPerSm), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
+        chnorm_bwd_kernel<4><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_bwd_kernel<1><<<ofr::grid_for(n, kThreads, kCtasPerSm), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
+        chnorm_bwd_kernel<1><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;

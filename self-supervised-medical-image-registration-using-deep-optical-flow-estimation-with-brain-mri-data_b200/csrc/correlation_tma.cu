@@ -50,8 +50,9 @@ __global__ void __launch_bounds__(FwdT<TH, NS, CK, NST>::THREADS, 1)
     corr_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                         float* __restrict__ out, CorrGeom g, int tiles_x, int tiles_y) {
     using T = FwdT<TH, NS, CK, NST>;
-    extern __shared__ unsigned char smem_raw[];
-    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // round the base up to 1024 B with an offset (not an integer cast) so the pointer stays in the shared window: LDS, not LD
+    float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::STAGE * NST);
 
     int bid = blockIdx.x;
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(BwdT<NS, SHIFTED>::THREADS, 1)
     corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapG,
                         float* __restrict__ gI, CorrGeom g, int tiles_x, int tiles_y, int cblocks) {
     using T = BwdT<NS, SHIFTED>;
-    extern __shared__ unsigned char smem_raw[];
-    float* Fs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Fs = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
     float* Gs = Fs + T::FT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(Gs + 2 * T::GS);  // [0],[1]: gradient stages, [2]: feature tile
 

@@ -1,16 +1,19 @@
 // Fused multi-scale self-supervised loss (replaces the eager OFEloss, loss.py:66-84, and its terms
 // photometric_loss :9-13, smoothness_loss :23-30, charbonnier :33-35, correlation_loss :52-64).
 //
-// Forward  : ONE launch streams every scale once.  Per pixel it resamples the full-resolution fixed image
-//            to the scale (bilinear, align_corners=False -- the F.interpolate of loss.py:11,54 folded in),
-//            and accumulates, in float64, the seven sums that the three terms need:
+// Forward  : ONE launch streams every scale once.  A CTA owns a strip of rows of one image of one scale
+//            (no per-pixel divisions); a thread owns 4 consecutive pixels (128-bit loads of warped / flow).
+//            Per pixel it resamples the full-resolution fixed image to the scale (bilinear,
+//            align_corners=False -- the F.interpolate of loss.py:11,54 folded in) and accumulates the seven
+//            sums the three terms need:
 //              sum charb(f-w), sum w, sum f, sum w^2, sum f^2, sum w*f, sum (charb(dv)+charb(dh))/2
 //            plus min/max of w and f (the reference's "centred tensor is identically zero" branch,
-//            loss.py:58-60, fires exactly when a tensor is constant).  CTA partials go to the workspace;
-//            a second one-CTA launch adds them in a fixed order, forms the per-scale terms and the
-//            weighted totals (weights 0.05*(i+1), float64, as in loss.py:71).  No atomics anywhere:
-//            bitwise reproducible.  Algorithmic bytes per scale: 4*B*h*w*(1 warped + 2 flow) + the taps
-//            of `fixed` (<= 4*B*Hs*Ws, L2-resident across scales).
+//            loss.py:58-60, fires exactly when a tensor is constant).  The 4 pixels of a thread are summed
+//            in float32, everything above that in float64.  CTA partials go to the workspace; a second
+//            one-CTA launch adds them in a fixed order, forms the per-scale terms and the weighted totals
+//            (weights 0.05*(i+1), float64, as in loss.py:71).  No atomics: bitwise reproducible.
+//            Algorithmic bytes per scale: 4*B*h*w*(1 warped + 2 flow) + the taps of `fixed`
+//            (<= 4*B*Hs*Ws, L2-resident across scales).
 // Backward : ONE launch, elementwise over every scale, using the moments kept in `state`.
 //            d/d warped gets the photometric and NCC terms, d/d flow the smoothness term; `fixed`
 //            is an input image and receives no gradient (it never requires one in the reference).
@@ -19,8 +22,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxCtasPerScale = 296;  // two waves of the 148 SMs
-constexpr int kPixPerCta = 2048;
+constexpr int kMaxCtasPerScale = 1184;  // eight CTAs per SM on the 148 SMs
+constexpr int kHardMaxCtasPerScale = 8192;  // batches beyond this many images per scale are refused
 constexpr int kNumPart = 11;           // partial slots per CTA, see enum
 
 enum { P_PHOTO = 0, P_SW, P_SF, P_SWW, P_SFF, P_SWF, P_SMOOTH, P_MINW, P_MAXW, P_MINF, P_MAXF };
@@ -34,6 +37,8 @@ struct ScaleDev {
     float* g_warped;
     float* g_flow;
     int h, w;
+    int rows_per_cta;  // work item = (image, strip of rows_per_cta rows)
+    int strips;        // strips per image
 };
 
 struct LossParams {
@@ -44,40 +49,47 @@ struct LossParams {
     int cta_begin[OFR_LOSS_MAX_SCALES + 1];  // CTA index range of each scale in the multi-scale launches
 };
 
-__device__ __forceinline__ float charb(float x) {  // (x^2 + (1e-9)^2)^0.25, float32 like the reference
-    return sqrtf(sqrtf(fmaf(x, x, 1e-18f)));
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
-__device__ __forceinline__ float charb_grad(float x) {  // d/dx = 0.5 * x * (x^2 + eps^2)^-0.75
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// (x^2 + (1e-9)^2)^0.25 in float32 like the reference; MUFU square roots (<= 2 ulp), far inside the 1e-5 budget
+__device__ __forceinline__ float charb(float x) { return sqrt_approx(sqrt_approx(fmaf(x, x, 1e-18f))); }
+// d/dx = 0.5 * x * (x^2 + eps^2)^-0.75
+__device__ __forceinline__ float charb_grad(float x) {
     const float s = fmaf(x, x, 1e-18f);
-    const float r = sqrtf(s);
-    return 0.5f * x / (r * sqrtf(r));
+    const float r = rsqrt_approx(s);          // s^-0.5
+    return 0.5f * x * r * sqrt_approx(r);     // s^-0.5 * s^-0.25
 }
 
 // F.interpolate(fixed, (h,w), mode='bilinear', align_corners=False) evaluated at one output pixel,
 // with ATen's index/weight arithmetic (area_pixel_compute_source_index).
-struct Resizer {
-    float sh, sw;
-    int Hs, Ws;
-    __device__ __forceinline__ Resizer(int Hs_, int Ws_, int h, int w) : Hs(Hs_), Ws(Ws_) {
-        sh = (float)Hs_ / (float)h;
-        sw = (float)Ws_ / (float)w;
-    }
-    __device__ __forceinline__ float at(const float* __restrict__ img, int y, int x) const {
-        float fy = __fsub_rn(__fmul_rn(sh, (float)y + 0.5f), 0.5f);
-        float fx = __fsub_rn(__fmul_rn(sw, (float)x + 0.5f), 0.5f);
-        fy = fy < 0.f ? 0.f : fy;
-        fx = fx < 0.f ? 0.f : fx;
-        const int y0 = min((int)fy, Hs - 1), x0 = min((int)fx, Ws - 1);
-        const int y1 = y0 + (y0 < Hs - 1), x1 = x0 + (x0 < Ws - 1);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        const float* r0 = img + (long long)y0 * Ws;
-        const float* r1 = img + (long long)y1 * Ws;
-        const float top = __fadd_rn(__fmul_rn(hx, __ldg(r0 + x0)), __fmul_rn(lx, __ldg(r0 + x1)));
-        const float bot = __fadd_rn(__fmul_rn(hx, __ldg(r1 + x0)), __fmul_rn(lx, __ldg(r1 + x1)));
-        return __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
-    }
+struct AxisTap {
+    int i0, i1;
+    float l0, l1;
 };
+__device__ __forceinline__ AxisTap axis_tap(float scale, int dst, int n) {
+    float f = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
+    f = f < 0.f ? 0.f : f;
+    AxisTap t;
+    t.i0 = min((int)f, n - 1);
+    t.i1 = t.i0 + (t.i0 < n - 1);
+    t.l1 = f - (float)t.i0;
+    t.l0 = 1.f - t.l1;
+    return t;
+}
+__device__ __forceinline__ float resize_at(const float* __restrict__ r0, const float* __restrict__ r1,
+                                           const AxisTap& ty, const AxisTap& tx) {
+    const float top = __fadd_rn(__fmul_rn(tx.l0, __ldg(r0 + tx.i0)), __fmul_rn(tx.l1, __ldg(r0 + tx.i1)));
+    const float bot = __fadd_rn(__fmul_rn(tx.l0, __ldg(r1 + tx.i0)), __fmul_rn(tx.l1, __ldg(r1 + tx.i1)));
+    return __fadd_rn(__fmul_rn(ty.l0, top), __fmul_rn(ty.l1, bot));
+}
 
 __device__ __forceinline__ int scale_of_cta(const LossParams& p, int cta) {
     int s = 0;
@@ -90,64 +102,121 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
 }
-__device__ __forceinline__ double warp_min(double v) {
+__device__ __forceinline__ float warp_minf(float v) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+    for (int d = 16; d > 0; d >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, d));
     return v;
 }
-__device__ __forceinline__ double warp_max(double v) {
+__device__ __forceinline__ float warp_maxf(float v) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
     return v;
+}
+
+// Work decomposition shared by forward and backward: CTA -> (scale, image b, row strip); threads sweep the
+// strip as (row, group of VEC pixels).  VEC = 4 when w % 4 == 0 (always true for the reference's scales >= 4).
+struct Strip {
+    int s, b, y0, y1;
+};
+__device__ __forceinline__ Strip strip_of_cta(const LossParams& p) {
+    Strip st;
+    st.s = scale_of_cta(p, blockIdx.x);
+    const ScaleDev& sc = p.sc[st.s];
+    const int item = blockIdx.x - p.cta_begin[st.s];
+    st.b = item / sc.strips;
+    st.y0 = (item - st.b * sc.strips) * sc.rows_per_cta;
+    st.y1 = min(st.y0 + sc.rows_per_cta, sc.h);
+    return st;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+    if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x, v[1 % VEC] = t.y, v[2 % VEC] = t.z, v[3 % VEC] = t.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void partial_body(const LossParams& p, const Strip& st, float (&f32)[7], float (&mm)[4],
+                                             double (&acc)[7]) {
+    const ScaleDev sc = p.sc[st.s];
+    const int h = sc.h, w = sc.w, gw = w / VEC;
+    const float sh = (float)p.Hs / (float)h, sw = (float)p.Ws / (float)w;
+    const float* fixed = p.fixed + (long long)st.b * p.Hs * p.Ws;
+    const float* wp = sc.warped + (long long)st.b * h * w;
+    const float* fl = sc.flow + (long long)st.b * 2 * h * w;
+    const int items = (st.y1 - st.y0) * gw;
+    for (int it = threadIdx.x; it < items; it += kThreads) {
+        const int ry = it / gw, y = st.y0 + ry, x = (it - ry * gw) * VEC;
+        const AxisTap ty = axis_tap(sh, y, p.Hs);
+        const float* r0 = fixed + (long long)ty.i0 * p.Ws;
+        const float* r1 = fixed + (long long)ty.i1 * p.Ws;
+        float wv[VEC], u[VEC], v[VEC], ud[VEC], vd[VEC];
+        const long long o = (long long)y * w + x;
+        load_vec<VEC>(wp + o, wv);
+        load_vec<VEC>(fl + o, u);
+        load_vec<VEC>(fl + (long long)h * w + o, v);
+        if (y + 1 < h) {
+            load_vec<VEC>(fl + o + w, ud);
+            load_vec<VEC>(fl + (long long)h * w + o + w, vd);
+        } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) ud[k] = vd[k] = 0.f;
+        }
+        const float ur = (x + VEC < w) ? __ldg(fl + o + VEC) : 0.f;                       // right neighbour of the last pixel
+        const float vr = (x + VEC < w) ? __ldg(fl + (long long)h * w + o + VEC) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) f32[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float fv = resize_at(r0, r1, ty, axis_tap(sw, x + k, p.Ws));
+            const float a = wv[k];
+            f32[P_PHOTO] += charb(__fsub_rn(fv, a));
+            f32[P_SW] += a;
+            f32[P_SF] += fv;
+            f32[P_SWW] = fmaf(a, a, f32[P_SWW]);
+            f32[P_SFF] = fmaf(fv, fv, f32[P_SFF]);
+            f32[P_SWF] = fmaf(a, fv, f32[P_SWF]);
+            mm[0] = fminf(mm[0], a), mm[1] = fmaxf(mm[1], a), mm[2] = fminf(mm[2], fv), mm[3] = fmaxf(mm[3], fv);
+            const float un = (k + 1 < VEC) ? u[(k + 1) % VEC] : ur;
+            const float vn = (k + 1 < VEC) ? v[(k + 1) % VEC] : vr;
+            const float sm = __fadd_rn(charb(__fsub_rn(u[k], ud[k])), charb(__fsub_rn(u[k], un))) +
+                             __fadd_rn(charb(__fsub_rn(v[k], vd[k])), charb(__fsub_rn(v[k], vn)));
+            f32[P_SMOOTH] = fmaf(sm, 0.5f, f32[P_SMOOTH]);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[k] += (double)f32[k];
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) loss_partial_kernel(const __grid_constant__ LossParams p,
                                                                 double* __restrict__ partials) {
     __shared__ double red[kNumPart][kThreads / 32];
-    const int s = scale_of_cta(p, blockIdx.x);
-    const ScaleDev sc = p.sc[s];
-    const int cta = blockIdx.x - p.cta_begin[s], nctas = p.cta_begin[s + 1] - p.cta_begin[s];
-    const int h = sc.h, w = sc.w;
-    const long long hw = (long long)h * w, total = (long long)p.B * hw;
-    const Resizer rz(p.Hs, p.Ws, h, w);
-
-    double a[kNumPart];
+    const Strip st = strip_of_cta(p);
+    double acc[7];
+    float f32[7], mm[4] = {3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f};
 #pragma unroll
-    for (int k = 0; k < kNumPart; ++k) a[k] = 0.0;
-    a[P_MINW] = a[P_MINF] = 1e300;
-    a[P_MAXW] = a[P_MAXF] = -1e300;
-
-    for (long long i = (long long)cta * kThreads + threadIdx.x; i < total; i += (long long)nctas * kThreads) {
-        const int b = (int)(i / hw);
-        const int rem = (int)(i - (long long)b * hw);
-        const int y = rem / w, x = rem - y * w;
-        const float wv = __ldg(sc.warped + i);
-        const float fv = rz.at(p.fixed + (long long)b * p.Hs * p.Ws, y, x);
-        a[P_PHOTO] += (double)charb(__fsub_rn(fv, wv));
-        a[P_SW] += (double)wv;
-        a[P_SF] += (double)fv;
-        a[P_SWW] += (double)wv * (double)wv;
-        a[P_SFF] += (double)fv * (double)fv;
-        a[P_SWF] += (double)wv * (double)fv;
-        a[P_MINW] = fmin(a[P_MINW], (double)wv);
-        a[P_MAXW] = fmax(a[P_MAXW], (double)wv);
-        a[P_MINF] = fmin(a[P_MINF], (double)fv);
-        a[P_MAXF] = fmax(a[P_MAXF], (double)fv);
-        const float* fl = sc.flow + (long long)b * 2 * hw + rem;
-        float sm = 0.f;
+    for (int k = 0; k < 7; ++k) acc[k] = 0.0;
+    if (p.sc[st.s].w % 4 == 0)
+        partial_body<4>(p, st, f32, mm, acc);
+    else
+        partial_body<1>(p, st, f32, mm, acc);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const float v = __ldg(fl + c * hw);
-            const float dn = (y + 1 < h) ? __ldg(fl + c * hw + w) : 0.f;
-            const float rt = (x + 1 < w) ? __ldg(fl + c * hw + 1) : 0.f;
-            sm += __fadd_rn(charb(__fsub_rn(v, dn)), charb(__fsub_rn(v, rt)));
-        }
-        a[P_SMOOTH] += (double)(sm * 0.5f);
-    }
-#pragma unroll
-    for (int k = 0; k < kNumPart; ++k) {
-        double v = (k == P_MINW || k == P_MINF) ? warp_min(a[k]) : (k == P_MAXW || k == P_MAXF) ? warp_max(a[k]) : warp_sum(a[k]);
+    for (int k = 0; k < 7; ++k) {
+        const double v = warp_sum(acc[k]);
         if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    {
+        const float a = warp_minf(mm[0]), b = warp_maxf(mm[1]), c = warp_minf(mm[2]), d = warp_maxf(mm[3]);
+        if ((threadIdx.x & 31) == 0) {
+            red[P_MINW][threadIdx.x >> 5] = a;
+            red[P_MAXW][threadIdx.x >> 5] = b;
+            red[P_MINF][threadIdx.x >> 5] = c;
+            red[P_MAXF][threadIdx.x >> 5] = d;
+        }
     }
     __syncthreads();
     if (threadIdx.x < kNumPart) {
@@ -161,20 +230,43 @@ __global__ void __launch_bounds__(kThreads) loss_partial_kernel(const __grid_con
     }
 }
 
-// One CTA: warp s reduces scale s (lane k = slot k, fixed CTA order), then thread 0 forms the terms.
-__global__ void __launch_bounds__(32 * OFR_LOSS_MAX_SCALES) loss_final_kernel(const __grid_constant__ LossParams p,
-                                                                              const double* __restrict__ partials,
-                                                                              double* __restrict__ state,
-                                                                              double* __restrict__ out4) {
-    const int s = threadIdx.x >> 5, k = threadIdx.x & 31;
-    if (s < p.n && k < kNumPart) {
-        const int c0 = p.cta_begin[s], c1 = p.cta_begin[s + 1];
-        double v = partials[(long long)c0 * kNumPart + k];
-        for (int c = c0 + 1; c < c1; ++c) {
-            const double t = partials[(long long)c * kNumPart + k];
-            v = (k == P_MINW || k == P_MINF) ? fmin(v, t) : (k == P_MAXW || k == P_MAXF) ? fmax(v, t) : v + t;
+// One CTA of 1024 threads: 128 threads per scale.  Thread t of a scale folds CTA partials t, t+128, ... in
+// ascending order, then a fixed-shape shuffle / shared-memory tree combines the 128 lanes: deterministic.
+__global__ void __launch_bounds__(1024) loss_final_kernel(const __grid_constant__ LossParams p,
+                                                          const double* __restrict__ partials,
+                                                          double* __restrict__ state, double* __restrict__ out4) {
+    __shared__ double red[OFR_LOSS_MAX_SCALES][4][kNumPart];
+    const int s = threadIdx.x >> 7, t = threadIdx.x & 127, wq = t >> 5;
+    double v[kNumPart];
+#pragma unroll
+    for (int k = 0; k < kNumPart; ++k) v[k] = (k == P_MINW || k == P_MINF) ? 1e300 : (k == P_MAXW || k == P_MAXF) ? -1e300 : 0.0;
+    if (s < p.n) {
+        for (int c = p.cta_begin[s] + t; c < p.cta_begin[s + 1]; c += 128) {
+#pragma unroll
+            for (int k = 0; k < kNumPart; ++k) {
+                const double x = partials[(long long)c * kNumPart + k];
+                v[k] = (k == P_MINW || k == P_MINF) ? fmin(v[k], x) : (k == P_MAXW || k == P_MAXF) ? fmax(v[k], x) : v[k] + x;
+            }
         }
-        state[s * OFR_LOSS_STATE_DOUBLES + k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < kNumPart; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double x = __shfl_xor_sync(0xffffffffu, v[k], d);
+            v[k] = (k == P_MINW || k == P_MINF) ? fmin(v[k], x) : (k == P_MAXW || k == P_MAXF) ? fmax(v[k], x) : v[k] + x;
+        }
+        if ((t & 31) == 0) red[s][wq][k] = v[k];
+    }
+    __syncthreads();
+    if (s < p.n && t < kNumPart) {
+        const int k = t;
+        double x = red[s][0][k];
+        for (int q = 1; q < 4; ++q) {
+            const double y = red[s][q][k];
+            x = (k == P_MINW || k == P_MINF) ? fmin(x, y) : (k == P_MAXW || k == P_MAXF) ? fmax(x, y) : x + y;
+        }
+        state[s * OFR_LOSS_STATE_DOUBLES + k] = x;
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
@@ -206,56 +298,92 @@ __global__ void __launch_bounds__(32 * OFR_LOSS_MAX_SCALES) loss_final_kernel(co
     out4[3] = P + S + C;  // loss.py:83 adds in this order
 }
 
-__global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const __grid_constant__ LossParams p,
-                                                            const double* __restrict__ grad4,
-                                                            const double* __restrict__ state) {
-    const int s = scale_of_cta(p, blockIdx.x);
-    const ScaleDev sc = p.sc[s];
-    const int cta = blockIdx.x - p.cta_begin[s], nctas = p.cta_begin[s + 1] - p.cta_begin[s];
-    const int h = sc.h, w = sc.w;
-    const long long hw = (long long)h * w, total = (long long)p.B * hw;
-    const Resizer rz(p.Hs, p.Ws, h, w);
-    const double* st = state + s * OFR_LOSS_STATE_DOUBLES;
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
+    if (VEC == 4)
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
+    else
+        p[0] = v[0];
+}
 
-    const double wi = 0.05 * (double)(s + 1), inv_n = 1.0 / (double)p.n, Bd = (double)p.B;
-    const double gP = grad4[0] + grad4[3], gC = grad4[1] + grad4[3], gS = grad4[2] + grad4[3];
-    const float cp = (float)(gP * inv_n * p.gamma * wi / Bd);          // d total / d photometric-sum
-    const float cs = (float)(gS * inv_n * p.lamb_da * wi / (2.0 * Bd));  // d total / d smoothness-sum
-    // NCC: d(1 - corr)/dw_i = -(1/B) * [ vy_i / sqrt(sxx*syy) - sxy * vx_i / (sxx^1.5 * syy^0.5) ]
-    const double N = st[S_N], mw = st[S_SW] / N, mf = st[S_SF] / N;
-    const double sxx = st[S_SWW] - N * mw * mw, syy = st[S_SFF] - N * mf * mf, sxy = st[S_SWF] - N * mw * mf;
-    const bool degenerate = st[S_DEGENERATE] != 0.0;
-    const double cc = degenerate ? 0.0 : -(gC * inv_n * p.zeta * wi / Bd);
-    const double k1 = degenerate ? 0.0 : cc / (sqrt(sxx) * sqrt(syy));
-    const double k2 = degenerate ? 0.0 : cc * sxy / (sxx * sqrt(sxx) * sqrt(syy));
-
-    for (long long i = (long long)cta * kThreads + threadIdx.x; i < total; i += (long long)nctas * kThreads) {
-        const int b = (int)(i / hw);
-        const int rem = (int)(i - (long long)b * hw);
-        const int y = rem / w, x = rem - y * w;
+template <int VEC>
+__device__ __forceinline__ void bwd_body(const LossParams& p, const Strip& st, float cp, float cs, float k1, float k2,
+                                         float mf, float mw) {
+    const ScaleDev sc = p.sc[st.s];
+    const int h = sc.h, w = sc.w, gw = w / VEC;
+    const long long hw = (long long)h * w;
+    const float sh = (float)p.Hs / (float)h, sw = (float)p.Ws / (float)w;
+    const float* fixed = p.fixed + (long long)st.b * p.Hs * p.Ws;
+    const int items = (st.y1 - st.y0) * gw;
+    for (int it = threadIdx.x; it < items; it += kThreads) {
+        const int ry = it / gw, y = st.y0 + ry, x = (it - ry * gw) * VEC;
+        const long long o = (long long)y * w + x;
         if (sc.g_warped) {
-            const float wv = __ldg(sc.warped + i);
-            const float fv = rz.at(p.fixed + (long long)b * p.Hs * p.Ws, y, x);
-            const float gph = -cp * charb_grad(__fsub_rn(fv, wv));
-            const double gn = k1 * ((double)fv - mf) - k2 * ((double)wv - mw);
-            sc.g_warped[i] = gph + (float)gn;
+            const AxisTap ty = axis_tap(sh, y, p.Hs);
+            const float* r0 = fixed + (long long)ty.i0 * p.Ws;
+            const float* r1 = fixed + (long long)ty.i1 * p.Ws;
+            float wv[VEC], g[VEC];
+            load_vec<VEC>(sc.warped + (long long)st.b * hw + o, wv);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float fv = resize_at(r0, r1, ty, axis_tap(sw, x + k, p.Ws));
+                // photometric: -cp * psi(f - w);  NCC: k1 * (f - mean f) - k2 * (w - mean w)
+                g[k] = fmaf(-cp, charb_grad(__fsub_rn(fv, wv[k])), fmaf(k1, fv - mf, -k2 * (wv[k] - mw)));
+            }
+            store_vec<VEC>(sc.g_warped + (long long)st.b * hw + o, g);
         }
         if (sc.g_flow) {
-            const float* fl = sc.flow + (long long)b * 2 * hw + rem;
-            float* gf = sc.g_flow + (long long)b * 2 * hw + rem;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const float* f = fl + c * hw;
-                const float v = __ldg(f);
-                const float dn = (y + 1 < h) ? __ldg(f + w) : 0.f;
-                const float rt = (x + 1 < w) ? __ldg(f + 1) : 0.f;
-                float g = charb_grad(__fsub_rn(v, dn)) + charb_grad(__fsub_rn(v, rt));
-                if (y > 0) g -= charb_grad(__fsub_rn(__ldg(f - w), v));
-                if (x > 0) g -= charb_grad(__fsub_rn(__ldg(f - 1), v));
-                gf[c * hw] = cs * g;
+                const float* f = sc.flow + ((long long)st.b * 2 + c) * hw + o;
+                float v[VEC], dn[VEC], up[VEC], g[VEC];
+                load_vec<VEC>(f, v);
+                if (y + 1 < h) {
+                    load_vec<VEC>(f + w, dn);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) dn[k] = 0.f;
+                }
+                if (y > 0) load_vec<VEC>(f - w, up);
+                const float rt = (x + VEC < w) ? __ldg(f + VEC) : 0.f;
+                const float lf = (x > 0) ? __ldg(f - 1) : 0.f;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float right = (k + 1 < VEC) ? v[(k + 1) % VEC] : rt;
+                    float gg = charb_grad(__fsub_rn(v[k], dn[k])) + charb_grad(__fsub_rn(v[k], right));
+                    if (y > 0) gg -= charb_grad(__fsub_rn(up[k], v[k]));
+                    if (k > 0)
+                        gg -= charb_grad(__fsub_rn(v[(k + VEC - 1) % VEC], v[k]));
+                    else if (x > 0)
+                        gg -= charb_grad(__fsub_rn(lf, v[k]));
+                    g[k] = cs * gg;
+                }
+                store_vec<VEC>(sc.g_flow + ((long long)st.b * 2 + c) * hw + o, g);
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const __grid_constant__ LossParams p,
+                                                            const double* __restrict__ grad4,
+                                                            const double* __restrict__ state) {
+    const Strip st = strip_of_cta(p);
+    const double* sd = state + st.s * OFR_LOSS_STATE_DOUBLES;
+    const double wi = 0.05 * (double)(st.s + 1), inv_n = 1.0 / (double)p.n, Bd = (double)p.B;
+    const double gP = grad4[0] + grad4[3], gC = grad4[1] + grad4[3], gS = grad4[2] + grad4[3];
+    const float cp = (float)(gP * inv_n * p.gamma * wi / Bd);            // d total / d photometric-sum
+    const float cs = (float)(gS * inv_n * p.lamb_da * wi / (2.0 * Bd));  // d total / d smoothness-sum
+    // NCC: d(1 - corr)/dw_i = -(1/B) * [ vy_i / sqrt(sxx*syy) - sxy * vx_i / (sxx^1.5 * syy^0.5) ]
+    const double N = sd[S_N], mw = sd[S_SW] / N, mf = sd[S_SF] / N;
+    const double sxx = sd[S_SWW] - N * mw * mw, syy = sd[S_SFF] - N * mf * mf, sxy = sd[S_SWF] - N * mw * mf;
+    const bool degenerate = sd[S_DEGENERATE] != 0.0;
+    const double cc = degenerate ? 0.0 : -(gC * inv_n * p.zeta * wi / Bd);
+    const float k1 = degenerate ? 0.f : (float)(cc / (sqrt(sxx) * sqrt(syy)));
+    const float k2 = degenerate ? 0.f : (float)(cc * sxy / (sxx * sqrt(sxx) * sqrt(syy)));
+    if (p.sc[st.s].w % 4 == 0)
+        bwd_body<4>(p, st, cp, cs, k1, k2, (float)mf, (float)mw);
+    else
+        bwd_body<1>(p, st, cp, cs, k1, k2, (float)mf, (float)mw);
 }
 
 int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const ofr_loss_scale_t* scales, int n,
@@ -271,12 +399,20 @@ int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const 
             const ofr_loss_scale_t& s = scales[i];
             if (!s.warped || !s.flow || s.h <= 0 || s.w <= 0) return OFR_EINVAL;
             if ((long long)s.h * s.w >= (1ll << 30)) return OFR_EINVAL;
-            p.sc[i] = ScaleDev{s.warped, s.flow, s.g_warped, s.g_flow, s.h, s.w};
-            long long pix = (long long)B * s.h * s.w;
-            long long nc = (pix + kPixPerCta - 1) / kPixPerCta;
-            at += (int)(nc < 1 ? 1 : (nc > kMaxCtasPerScale ? kMaxCtasPerScale : nc));
+            // strips of rows: ~2048 pixels per CTA, at most kMaxCtasPerScale CTAs per scale
+            int rows = (2048 + s.w - 1) / s.w;
+            if (rows < 1) rows = 1;
+            if (rows > s.h) rows = s.h;
+            int strips = (s.h + rows - 1) / rows;
+            while ((long long)strips * B > kMaxCtasPerScale && rows < s.h) {
+                rows = rows * 2 > s.h ? s.h : rows * 2;
+                strips = (s.h + rows - 1) / rows;
+            }
+            if ((long long)strips * B > kHardMaxCtasPerScale) return OFR_ENOTSUP;  // absurd batch size
+            p.sc[i] = ScaleDev{s.warped, s.flow, s.g_warped, s.g_flow, s.h, s.w, rows, strips};
+            at += strips * B;
         } else {
-            p.sc[i] = ScaleDev{nullptr, nullptr, nullptr, nullptr, 0, 0};
+            p.sc[i] = ScaleDev{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0};
         }
     }
     p.cta_begin[OFR_LOSS_MAX_SCALES] = at;
@@ -284,11 +420,15 @@ int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const 
     return OFR_OK;
 }
 
+size_t ws_bytes_for(int total_ctas) { return ofr::align_up(sizeof(double) * kNumPart * (size_t)total_ctas, 256); }
+
 }  // namespace
 
 extern "C" size_t ofr_loss_workspace(int n_scales) {
     if (n_scales < 1 || n_scales > OFR_LOSS_MAX_SCALES) return 0;
-    return ofr::align_up(sizeof(double) * kNumPart * (size_t)kMaxCtasPerScale * n_scales, 256);
+    // upper bound that does not depend on the batch: fill_params never uses more than kHardMaxCtasPerScale CTAs
+    // per scale (and more than kMaxCtasPerScale only for batches beyond 1184 images).
+    return ws_bytes_for(kHardMaxCtasPerScale * n_scales);
 }
 
 extern "C" int ofr_loss_fwd(const float* fixed, int B, int Hs, int Ws, const ofr_loss_scale_t* scales, int n_scales,
@@ -298,12 +438,12 @@ extern "C" int ofr_loss_fwd(const float* fixed, int B, int Hs, int Ws, const ofr
     int rc = fill_params(p, fixed, B, Hs, Ws, scales, n_scales, lamb_da, gamma, zeta);
     if (rc != OFR_OK) return rc;
     if (!out4 || !state) return OFR_EINVAL;
-    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < ofr_loss_workspace(n_scales)) return OFR_EWORKSPACE;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < ws_bytes_for(p.cta_begin[n_scales])) return OFR_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     double* partials = (double*)ws;
     loss_partial_kernel<<<p.cta_begin[n_scales], kThreads, 0, st>>>(p, partials);
     OFR_LAUNCH_CHECK();
-    loss_final_kernel<<<1, 32 * OFR_LOSS_MAX_SCALES, 0, st>>>(p, partials, state, out4);
+    loss_final_kernel<<<1, 1024, 0, st>>>(p, partials, state, out4);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }

@@ -130,54 +130,55 @@ constexpr int kFwdThreads = 256;
 constexpr int kFwdChunk = 8;  // channels per blockIdx.y slice
 
 template <int MODE, int PX>
-__global__ void __launch_bounds__(kFwdThreads) resample_fwd_kernel(const float* __restrict__ in1,
-                                                                   const float* __restrict__ flow,
-                                                                   float* __restrict__ out, WarpGeom g) {
+__global__ void __launch_bounds__(kFwdThreads, 3) resample_fwd_kernel(const float* __restrict__ in1,
+                                                                      const float* __restrict__ flow,
+                                                                      float* __restrict__ out, WarpGeom g) {
+    // one work item (PX consecutive pixels of a row) per thread: every CTA issues its flow loads at once and the
+    // block scheduler, not a grid-stride loop, keeps the SMs full -> more bytes in flight per SM
     const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
     const long long total = (long long)g.B * hwf / PX;
     const int c0 = blockIdx.y * kFwdChunk, c1 = min(c0 + kFwdChunk, g.C);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i * PX;
-        const int b = (int)(pix / hwf);
-        const int rem = (int)(pix - (long long)b * hwf);
-        const int y = rem / g.Wf, x = rem - y * g.Wf;
-        const float* fu = flow + (long long)b * 2 * hwf + rem;
-        float u[PX], v[PX];
-        if (PX == 4) {
-            float4 a = ofr::ldg4(fu), c = ofr::ldg4(fu + hwf);
-            u[0] = a.x, u[1 % PX] = a.y, u[2 % PX] = a.z, u[3 % PX] = a.w;
-            v[0] = c.x, v[1 % PX] = c.y, v[2 % PX] = c.z, v[3 % PX] = c.w;
-        } else {
-            u[0] = __ldg(fu);
-            v[0] = __ldg(fu + hwf);
-        }
-        Samp s[PX];
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long pix = i * PX;
+    const int b = (int)(pix / hwf);
+    const int rem = (int)(pix - (long long)b * hwf);
+    const int y = rem / g.Wf, x = rem - y * g.Wf;
+    const float* fu = flow + (long long)b * 2 * hwf + rem;
+    float u[PX], v[PX];
+    if (PX == 4) {
+        float4 a = ofr::ldg4(fu), c = ofr::ldg4(fu + hwf);
+        u[0] = a.x, u[1 % PX] = a.y, u[2 % PX] = a.z, u[3 % PX] = a.w;
+        v[0] = c.x, v[1 % PX] = c.y, v[2 % PX] = c.z, v[3 % PX] = c.w;
+    } else {
+        u[0] = __ldg(fu);
+        v[0] = __ldg(fu + hwf);
+    }
+    Samp s[PX];
 #pragma unroll
-        for (int k = 0; k < PX; ++k) s[k] = make_samp<MODE>(x + k, y, u[k], v[k], g);
-        for (int c = c0; c < c1; ++c) {
-            const float* img = in1 + ((long long)b * g.C + c) * hwi;
-            float r[PX];
+    for (int k = 0; k < PX; ++k) s[k] = make_samp<MODE>(x + k, y, u[k], v[k], g);
+    for (int c = c0; c < c1; ++c) {
+        const float* img = in1 + ((long long)b * g.C + c) * hwi;
+        float r[PX];
 #pragma unroll
-            for (int k = 0; k < PX; ++k) {
-                if (MODE == OFR_WARP_FLOWNET2_NEAREST) {
-                    // nearest tap: floor(x + u + 0.5), clamped
-                    const float xn = floorf(__fadd_rn(__fadd_rn((float)(x + k), u[k]), 0.5f));
-                    const float yn = floorf(__fadd_rn(__fadd_rn((float)y, v[k]), 0.5f));
-                    const int xi = min(max(safe_floor_int(xn, g.Win), 0), g.Win - 1);
-                    const int yi = min(max(safe_floor_int(yn, g.Hin), 0), g.Hin - 1);
-                    r[k] = __ldg(img + (long long)yi * g.Win + xi);
-                } else {
-                    Taps<MODE> t(s[k], g);
-                    r[k] = s[k].live ? bilerp<MODE>(img, s[k], t, g.Win) : 0.f;
-                }
+        for (int k = 0; k < PX; ++k) {
+            if (MODE == OFR_WARP_FLOWNET2_NEAREST) {
+                // nearest tap: floor(x + u + 0.5), clamped
+                const float xn = floorf(__fadd_rn(__fadd_rn((float)(x + k), u[k]), 0.5f));
+                const float yn = floorf(__fadd_rn(__fadd_rn((float)y, v[k]), 0.5f));
+                const int xi = min(max(safe_floor_int(xn, g.Win), 0), g.Win - 1);
+                const int yi = min(max(safe_floor_int(yn, g.Hin), 0), g.Hin - 1);
+                r[k] = __ldg(img + (long long)yi * g.Win + xi);
+            } else {
+                Taps<MODE> t(s[k], g);
+                r[k] = s[k].live ? bilerp<MODE>(img, s[k], t, g.Win) : 0.f;
             }
-            float* o = out + ((long long)b * g.C + c) * hwf + rem;
-            if (PX == 4)
-                ofr::stcs4(o, make_float4(r[0], r[1 % PX], r[2 % PX], r[3 % PX]));
-            else
-                o[0] = r[0];
         }
+        float* o = out + ((long long)b * g.C + c) * hwf + rem;
+        if (PX == 4)
+            ofr::stcs4(o, make_float4(r[0], r[1 % PX], r[2 % PX], r[3 % PX]));
+        else
+            o[0] = r[0];
     }
 }
 
@@ -266,6 +267,60 @@ __global__ void __launch_bounds__(32 * CG) resample_bwd_src_kernel(const float* 
     }
 }
 
+// Few-channel variant (C < 8: the full-resolution FlowNet2 / stn warps, C = 1): one thread owns 4 consecutive
+// source pixels, 128-bit loads of flow and gO, 128-bit store of the flow gradient; channels looped in the thread.
+template <int MODE, bool WANT_G2, bool WANT_BIN>
+__global__ void __launch_bounds__(256, 3) resample_bwd_src4_kernel(const float* __restrict__ in1,
+                                                                   const float* __restrict__ flow,
+                                                                   const float* __restrict__ gO,
+                                                                   float* __restrict__ gI2, int* __restrict__ counts,
+                                                                   int* __restrict__ key, int* __restrict__ rank,
+                                                                   WarpGeom g, float sx, float sy) {
+    const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
+    const long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= (long long)g.B * hwf / 4) return;
+    const long long pix = i * 4;
+    const int b = (int)(pix / hwf);
+    const int rem = (int)(pix - (long long)b * hwf);
+    const int y = rem / g.Wf, x = rem - y * g.Wf;
+    const float* fu = flow + (long long)b * 2 * hwf + rem;
+    const float4 fu4 = ofr::ldg4(fu), fv4 = ofr::ldg4(fu + hwf);
+    const float u[4] = {fu4.x, fu4.y, fu4.z, fu4.w}, v[4] = {fv4.x, fv4.y, fv4.z, fv4.w};
+    Samp s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = make_samp<MODE>(x + k, y, u[k], v[k], g);
+    if (WANT_BIN) {
+        int cells[4], ranks[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cells[k] = cell_of<MODE>(s[k], g);
+            ranks[k] = 0;
+            if (cells[k] >= 0) ranks[k] = atomicAdd(counts + (long long)b * (g.Hin + 1) * (g.Win + 1) + cells[k], 1);
+        }
+        *reinterpret_cast<int4*>(key + pix) = make_int4(cells[0], cells[1], cells[2], cells[3]);
+        *reinterpret_cast<int4*>(rank + pix) = make_int4(ranks[0], ranks[1], ranks[2], ranks[3]);
+    }
+    if (!WANT_G2) return;
+    float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < g.C; ++c) {
+        const float* img = in1 + ((long long)b * g.C + c) * hwi;
+        const float4 go4 = ofr::ldg4(gO + ((long long)b * g.C + c) * hwf + rem);
+        const float go[4] = {go4.x, go4.y, go4.z, go4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!s[k].live) continue;
+            Taps<MODE> t(s[k], g);
+            const float tl = t.fetch(img, t.yt, t.xl, g.Win), tr = t.fetch(img, t.yt, t.xr, g.Win);
+            const float bl = t.fetch(img, t.yb, t.xl, g.Win), br = t.fetch(img, t.yb, t.xr, g.Win);
+            ax[k] = fmaf(go[k], fmaf(s[k].wy1, br - bl, s[k].wy0 * (tr - tl)), ax[k]);
+            ay[k] = fmaf(go[k], fmaf(s[k].wx1, br - tr, s[k].wx0 * (bl - tl)), ay[k]);
+        }
+    }
+    float* o = gI2 + (long long)b * 2 * hwf + rem;
+    ofr::stcs4(o, make_float4(ax[0] * sx, ax[1] * sx, ax[2] * sx, ax[3] * sx));
+    ofr::stcs4(o + hwf, make_float4(ay[0] * sy, ay[1] * sy, ay[2] * sy, ay[3] * sy));
+}
+
 // ---- exclusive scan of the cell counts (three small kernels)
 __device__ __forceinline__ int warp_incl_scan(int v) {
 #pragma unroll
@@ -349,20 +404,35 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int* __r
     }
 }
 
-// ---- CSR fill: entries[offset[cell] + rank] = source index within its image
-__global__ void __launch_bounds__(256) resample_fill_kernel(const int* __restrict__ key, const int* __restrict__ rank,
+// ---- CSR fill.  An entry is a 16-byte record {source index within its image, (x0,y0) packed, wx1, wy1}: everything
+// the per-target gather needs about a source, so the gather never touches the flow again.
+__device__ __forceinline__ int pack_xy(int x0, int y0) { return ((y0 + 2) << 16) | (x0 + 2); }
+__device__ __forceinline__ void unpack_xy(int p, int& x0, int& y0) {
+    x0 = (p & 0xffff) - 2;
+    y0 = (p >> 16) - 2;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) resample_fill_kernel(const float* __restrict__ flow,
+                                                            const int* __restrict__ key, const int* __restrict__ rank,
                                                             const int* __restrict__ counts,
-                                                            const int* __restrict__ offsets, int* __restrict__ entries,
+                                                            const int* __restrict__ offsets, int4* __restrict__ entries,
                                                             int* __restrict__ heavy, int* __restrict__ heavy_n,
-                                                            long long total, int hwf, int cells_per_img) {
+                                                            WarpGeom g) {
+    const int hwf = g.Hf * g.Wf;
+    const long long total = (long long)g.B * hwf;
     const long long pix = blockIdx.x * 256ll + threadIdx.x;
     if (pix >= total) return;
     const int k = key[pix];
     if (k < 0) return;
     const int b = (int)(pix / hwf);
-    const int cell = b * cells_per_img + k;
+    const int src = (int)(pix - (long long)b * hwf);
+    const int cell = b * (g.Hin + 1) * (g.Win + 1) + k;
     const int r = rank[pix];
-    entries[offsets[cell] + r] = (int)(pix - (long long)b * hwf);
+    const int sy = src / g.Wf, sx = src - sy * g.Wf;
+    const float* fl = flow + (long long)b * 2 * hwf + src;
+    const Samp s = make_samp<MODE>(sx, sy, __ldg(fl), __ldg(fl + hwf), g);
+    entries[offsets[cell] + r] = make_int4(src, pack_xy(s.x0, s.y0), __float_as_int(s.wx1), __float_as_int(s.wy1));
     if (r == 0 && counts[cell] > kHeavy) heavy[atomicAdd(heavy_n, 1)] = cell;
 }
 
@@ -372,12 +442,12 @@ __global__ void __launch_bounds__(512) resample_sort_heavy_kernel(const int* __r
                                                                   const int* __restrict__ heavy_n,
                                                                   const int* __restrict__ counts,
                                                                   const int* __restrict__ offsets,
-                                                                  int* __restrict__ entries) {
+                                                                  int4* __restrict__ entries) {
     const int nh = *heavy_n;
     for (int h = blockIdx.x; h < nh; h += gridDim.x) {
         const int cell = heavy[h];
         const int n = counts[cell];
-        int* a = entries + offsets[cell];
+        int4* a = entries + offsets[cell];
         int P = 1;
         while (P < n) P <<= 1;
         for (int k = 2; k <= P; k <<= 1) {
@@ -385,8 +455,8 @@ __global__ void __launch_bounds__(512) resample_sort_heavy_kernel(const int* __r
                 for (int i = threadIdx.x; i < n; i += blockDim.x) {
                     const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
                     if (l > i && l < n) {
-                        const int vi = a[i], vl = a[l];
-                        if (vi > vl) {
+                        const int4 vi = a[i], vl = a[l];
+                        if (vi.x > vl.x) {
                             a[i] = vl;
                             a[l] = vi;
                         }
@@ -399,14 +469,13 @@ __global__ void __launch_bounds__(512) resample_sort_heavy_kernel(const int* __r
 }
 
 // ---- per-target gather of the adjoint.  Thread = one target pixel, blockIdx.y = channel chunk.
-constexpr int kTgtChunk = 8;
+constexpr int kTgtChunk = 16;
 
 template <int MODE>
-__global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __restrict__ flow,
-                                                               const float* __restrict__ gO,
+__global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __restrict__ gO,
                                                                const int* __restrict__ counts,
                                                                const int* __restrict__ offsets,
-                                                               const int* __restrict__ entries,
+                                                               const int4* __restrict__ entries,
                                                                float* __restrict__ gI1, WarpGeom g) {
     const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
     const long long tpix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -418,7 +487,6 @@ __global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __re
     const int nc = min(kTgtChunk, g.C - c0);
     const int cw = g.Win + 1;
     const long long cell_base = (long long)b * (g.Hin + 1) * cw;
-    const float* fl = flow + (long long)b * 2 * hwf;
     const float* go = gO + ((long long)b * g.C + c0) * hwf;
 
     float acc[kTgtChunk];
@@ -432,22 +500,28 @@ __global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __re
         const long long cell = cell_base + (long long)(ky + 1) * cw + (kx + 1);
         const int n = counts[cell];
         if (n == 0) continue;
-        const int* e = entries + offsets[cell];
+        const int4* e = entries + offsets[cell];
         int last = -1;
         for (int it = 0; it < n; ++it) {
-            int src;
+            int4 rec;
             if (n == 1 || n > kHeavy) {
-                src = e[it];  // single entry, or pre-sorted by resample_sort_heavy_kernel
-            } else {          // next entry in ascending source order
-                src = 0x7fffffff;
+                rec = __ldg(e + it);  // single entry, or pre-sorted by resample_sort_heavy_kernel
+            } else {                  // next entry in ascending source order
+                int best = 0x7fffffff, bj = 0;
                 for (int j = 0; j < n; ++j) {
-                    const int v = e[j];
-                    if (v > last && v < src) src = v;
+                    const int v = __ldg(&e[j].x);
+                    if (v > last && v < best) best = v, bj = j;
                 }
-                last = src;
+                rec = __ldg(e + bj);
+                last = best;
             }
-            const int sy = src / g.Wf, sx = src - sy * g.Wf;
-            const Samp s = make_samp<MODE>(sx, sy, __ldg(fl + src), __ldg(fl + hwf + src), g);
+            const int src = rec.x;
+            Samp s;
+            unpack_xy(rec.y, s.x0, s.y0);
+            s.wx1 = __int_as_float(rec.z);
+            s.wy1 = __int_as_float(rec.w);
+            s.wx0 = __fsub_rn(1.f, s.wx1);
+            s.wy0 = __fsub_rn(1.f, s.wy1);
             const Taps<MODE> t(s, g);
             // weight of each of the four taps if it lands on this target, else 0 (order TL, TR, BL, BR)
             const float w0 = (t.xl == tx && t.yt == ty) ? __fmul_rn(s.wx0, s.wy0) : 0.f;
@@ -499,7 +573,7 @@ WsLayout ws_layout(int B, int Hin, int Win, int Hf, int Wf) {
     L.blocksum = take(sizeof(int) * (size_t)L.nblk);
     L.key = take(sizeof(int) * (size_t)L.npix);
     L.rank = take(sizeof(int) * (size_t)L.npix);
-    L.entries = take(sizeof(int) * (size_t)L.npix);
+    L.entries = take(sizeof(int4) * (size_t)L.npix);
     L.heavy = take(sizeof(int) * (size_t)(L.npix / kHeavy + 1));
     L.total = o;
     return L;
@@ -510,6 +584,7 @@ bool geom_ok(int B, int C, int Hin, int Win, int Hf, int Wf) {
     // index arithmetic inside one image is 32-bit
     if ((long long)Hf * Wf >= (1ll << 30) || (long long)(Hin + 1) * (Win + 1) >= (1ll << 30)) return false;
     if ((long long)B * (Hin + 1) * (Win + 1) >= (1ll << 31)) return false;
+    if (Hin > 32000 || Win > 32000 || Hf > 32000 || Wf > 32000) return false;  // (x0, y0) are packed in 16 bits each
     return true;
 }
 
@@ -527,10 +602,10 @@ int launch_fwd(const float* in1, const float* flow, float* out, const WarpGeom& 
     const unsigned gy = (unsigned)((g.C + kFwdChunk - 1) / kFwdChunk);
     const bool vec = (g.Wf % 4 == 0) && ofr::aligned16(flow) && ofr::aligned16(out);
     if (vec) {
-        dim3 grid(ofr::grid_for(npix / 4, kFwdThreads, 8), gy);
+        dim3 grid((unsigned)((npix / 4 + kFwdThreads - 1) / kFwdThreads), gy);
         resample_fwd_kernel<MODE, 4><<<grid, kFwdThreads, 0, st>>>(in1, flow, out, g);
     } else {
-        dim3 grid(ofr::grid_for(npix, kFwdThreads, 8), gy);
+        dim3 grid((unsigned)((npix + kFwdThreads - 1) / kFwdThreads), gy);
         resample_fwd_kernel<MODE, 1><<<grid, kFwdThreads, 0, st>>>(in1, flow, out, g);
     }
     OFR_LAUNCH_CHECK();
@@ -573,12 +648,24 @@ int run_bwd(const float* in1, const float* flow, const float* gO, float* gI1, fl
     int* blocksum = want_bin ? (int*)(w + L.blocksum) : nullptr;
     int* key = want_bin ? (int*)(w + L.key) : nullptr;
     int* rank = want_bin ? (int*)(w + L.rank) : nullptr;
-    int* entries = want_bin ? (int*)(w + L.entries) : nullptr;
+    int4* entries = want_bin ? (int4*)(w + L.entries) : nullptr;
     int* heavy = want_bin ? (int*)(w + L.heavy) : nullptr;
     if (want_bin) OFR_CUDA(cudaMemsetAsync(w + L.counts, 0, L.offsets - L.counts, st));  // counts + misc
 
     int rc;
-    if (g.C >= 8)
+    const bool vec4 = g.C < 8 && (g.Wf % 4 == 0) && ofr::aligned16(flow) && ofr::aligned16(gO) &&
+                      (!gI2 || ofr::aligned16(gI2));
+    if (vec4) {
+        const long long n4 = (long long)g.B * g.Hf * g.Wf / 4;
+        const unsigned grid = (unsigned)((n4 + 255) / 256);
+        if (gI2 && want_bin)
+            resample_bwd_src4_kernel<MODE, true, true><<<grid, 256, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
+        else if (gI2)
+            resample_bwd_src4_kernel<MODE, true, false><<<grid, 256, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
+        else
+            resample_bwd_src4_kernel<MODE, false, true><<<grid, 256, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
+        rc = ofr::after_launch();
+    } else if (g.C >= 8)
         rc = launch_src<MODE, 8>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
     else
         rc = launch_src<MODE, 1>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
@@ -590,14 +677,14 @@ int run_bwd(const float* in1, const float* flow, const float* gO, float* gI1, fl
     OFR_LAUNCH_CHECK();
     scan_apply_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, offsets, L.ncell);
     OFR_LAUNCH_CHECK();
-    resample_fill_kernel<<<(unsigned)((L.npix + 255) / 256), 256, 0, st>>>(
-        key, rank, counts, offsets, entries, heavy, misc, L.npix, g.Hf * g.Wf, (g.Hin + 1) * (g.Win + 1));
+    resample_fill_kernel<MODE><<<(unsigned)((L.npix + 255) / 256), 256, 0, st>>>(flow, key, rank, counts, offsets,
+                                                                                entries, heavy, misc, g);
     OFR_LAUNCH_CHECK();
     resample_sort_heavy_kernel<<<ofr::sm_count(), 512, 0, st>>>(heavy, misc, counts, offsets, entries);
     OFR_LAUNCH_CHECK();
     const long long ntgt = (long long)g.B * g.Hin * g.Win;
     dim3 grid((unsigned)((ntgt + 127) / 128), (unsigned)((g.C + kTgtChunk - 1) / kTgtChunk));
-    resample_bwd_tgt_kernel<MODE><<<grid, 128, 0, st>>>(flow, gO, counts, offsets, entries, gI1, g);
+    resample_bwd_tgt_kernel<MODE><<<grid, 128, 0, st>>>(gO, counts, offsets, entries, gI1, g);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
