@@ -31,125 +31,200 @@ __host__ __device__ constexpr int pitch_for(int cols) {  // multiple of 4, == 4*
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int TH, int NS, int CK, int NST>
+// Persistent CTAs (one per SM) walk the (image, tile) list; the TMA ring runs ahead across tile boundaries, so the
+// loads of the next tile overlap the last chunks and the epilogue of the current one.
+//
+// Thread tile: M pixels along x  x  9 x-displacements of one displacement row tj  (acc[M][9], M = 16: 144 FMAs per
+// 10 128-bit LDS).  Shared-memory bandwidth is the scarce resource: a 128-bit LDS costs >= 4 wavefronts however many
+// lanes share an address, so the lane mapping is chosen to make every quarter-warp bank-conflict free:
+//   warps 0..  : lanes = 8 tj (fastest) x 4 (strip,row) pairs.  A quarter-warp = the 8 tj rows of one strip; the f2 row
+//                pitch is 4*odd (mod 32) floats, so the 8 rows start in 8 different bank groups.
+//   last warp(s): tj = 8, lanes = 8 rows (fastest) x strips, same argument with the f1 pitch (also 4*odd mod 32).
+template <int M, int TH, int NS, int CK, int NST>
 struct FwdT {
-    static constexpr int TW = NS * kM;
+    static constexpr int TW = NS * M;
+    static constexpr int P1 = pitch_for(TW);
     static constexpr int P2 = pitch_for(TW + 2 * kR);
     static constexpr int R2 = TH + 2 * kR;
-    static constexpr int F1 = CK * TH * TW;   // floats per stage
+    static constexpr int F1 = CK * TH * P1;   // floats per stage
     static constexpr int F2 = CK * R2 * P2;
     static constexpr int STAGE = F1 + F2;
-    static constexpr int THREADS = kD * NS * TH;
-    static constexpr size_t SMEM = sizeof(float) * STAGE * NST + 8 * NST + 1024;
-    static_assert((F1 * 4) % 128 == 0 && (F2 * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
-    static_assert(THREADS <= 1024, "CTA too large");
+    static constexpr int T1 = 8 * TH * NS;    // threads that own tj = 0..7
+    static constexpr int THREADS = kD * TH * NS;
+    static constexpr int OP = TH * TW;        // one output plane tile, floats
+    static constexpr int OS = kD * OP;        // epilogue staging buffer: the 9 planes {tj*9 + j} of one j
+    static constexpr size_t SMEM = sizeof(float) * (STAGE * NST + 2 * OS) + 8 * NST + 1024;
+    static_assert((F1 * 4) % 128 == 0 && (F2 * 4) % 128 == 0 && (OP * 4) % 128 == 0,
+                  "TMA sources / destinations must stay 128-byte aligned");
+    static_assert(M % 4 == 0 && THREADS <= 1024, "bad tile");
 };
 
-template <int TH, int NS, int CK, int NST>
-__global__ void __launch_bounds__(FwdT<TH, NS, CK, NST>::THREADS, 1)
+template <int M, int TH, int NS, int CK, int NST>
+__global__ void __maxnreg__(224)
     corr_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                        float* __restrict__ out, CorrGeom g, int tiles_x, int tiles_y) {
-    using T = FwdT<TH, NS, CK, NST>;
+                        const __grid_constant__ CUtensorMap mapO, CorrGeom g, int tiles_x, int tiles_y) {
+    using T = FwdT<M, TH, NS, CK, NST>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // round the base up to 1024 B with an offset (not an integer cast) so the pointer stays in the shared window: LDS, not LD
     float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::STAGE * NST);
-
-    int bid = blockIdx.x;
-    const int txi = bid % tiles_x;
-    bid /= tiles_x;
-    const int tyi = bid % tiles_y;
-    const int b = bid / tiles_y;
-    const int x0 = txi * T::TW, y0 = tyi * TH;
+    float* ostage = smem + T::STAGE * NST;  // [2][9][TH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + 2 * T::OS);
 
     const int tid = threadIdx.x;
-    const int tjl = tid % kD;
-    const int s = (tid / kD) % NS;
-    const int row = tid / (kD * NS);
+    int tj, s, row;
+    if (tid < T::T1) {
+        tj = tid & 7;
+        const int q = tid >> 3;
+        s = q % NS;
+        row = q / NS;
+    } else {
+        tj = 8;
+        const int q = tid - T::T1;
+        row = q % TH;
+        s = q / TH;
+    }
 
     const int nchunks = (g.C + CK - 1) / CK;
-    auto issue = [&](int chunk, int st) {
+    const int ntiles = tiles_x * tiles_y * g.B;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total = my_tiles * nchunks;  // ring iterations of this CTA
+
+    auto tile_origin = [&](int k, int& x0, int& y0, int& b) {  // k-th tile of this CTA
+        int t = blockIdx.x + k * gridDim.x;
+        x0 = (t % tiles_x) * T::TW;
+        t /= tiles_x;
+        y0 = (t % tiles_y) * TH;
+        b = t / tiles_y;
+    };
+    auto issue = [&](int q) {
+        int x0, y0, b;
+        tile_origin(q / nchunks, x0, y0, b);
+        const int c0 = (q % nchunks) * CK, st = q % NST;
         float* dst = smem + st * T::STAGE;
         ofr::mbar_expect_tx(&bars[st], T::STAGE * 4);
-        ofr::tma_load_4d(dst, &map1, &bars[st], x0, y0, chunk * CK, b);
-        ofr::tma_load_4d(dst + T::F1, &map2, &bars[st], x0 - kR, y0 - kR, chunk * CK, b);
+        ofr::tma_load_4d(dst, &map1, &bars[st], x0, y0, c0, b);
+        ofr::tma_load_4d(dst + T::F1, &map2, &bars[st], x0 - kR, y0 - kR, c0, b);
     };
     if (tid == 0) {
         ofr::tma_prefetch_desc(&map1);
         ofr::tma_prefetch_desc(&map2);
+        ofr::tma_prefetch_desc(&mapO);
         for (int i = 0; i < NST; ++i) ofr::mbar_init(&bars[i], 1);
         ofr::mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0)
-        for (int i = 0; i < NST && i < nchunks; ++i) issue(i, i);
+        for (int i = 0; i < NST && i < total; ++i) issue(i);
 
-    float acc[kM][kD];
+    float acc[M][kD];
 #pragma unroll
-    for (int i = 0; i < kM; ++i)
+    for (int i = 0; i < M; ++i)
 #pragma unroll
         for (int j = 0; j < kD; ++j) acc[i][j] = 0.f;
 
-    for (int ck = 0; ck < nchunks; ++ck) {
-        const int st = ck % NST;
-        ofr::mbar_wait(&bars[st], (ck / NST) & 1);
-        const float* ap = smem + st * T::STAGE + row * T::TW + s * kM;
-        const float* bp = smem + st * T::STAGE + T::F1 + (row + tjl) * T::P2 + s * kM;
+    int ck = 0, tile_k = 0;
+    for (int q = 0; q < total; ++q) {
+        const int st = q % NST;
+        ofr::mbar_wait(&bars[st], (q / NST) & 1);
+        const float* ap = smem + st * T::STAGE + row * T::P1 + s * M;
+        const float* bp = smem + st * T::STAGE + T::F1 + (row + tj) * T::P2 + s * M;
 #pragma unroll 1
         for (int cc = 0; cc < CK; ++cc) {
-            float a[kM], bv[kM + 2 * kR];
+            float a[M], bv[M + 2 * kR];
 #pragma unroll
-            for (int i = 0; i < kM; i += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(ap + cc * TH * T::TW + i);
+            for (int i = 0; i < M; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(ap + cc * TH * T::P1 + i);
                 a[i] = v.x, a[i + 1] = v.y, a[i + 2] = v.z, a[i + 3] = v.w;
             }
 #pragma unroll
-            for (int i = 0; i < kM + 2 * kR; i += 4) {
+            for (int i = 0; i < M + 2 * kR; i += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(bp + cc * T::R2 * T::P2 + i);
                 bv[i] = v.x, bv[i + 1] = v.y, bv[i + 2] = v.z, bv[i + 3] = v.w;
             }
 #pragma unroll
-            for (int i = 0; i < kM; ++i)
+            for (int i = 0; i < M; ++i)
 #pragma unroll
                 for (int j = 0; j < kD; ++j) acc[i][j] = fmaf(a[i], bv[i + j], acc[i][j]);
         }
         __syncthreads();  // every thread is done reading stage st
-        if (tid == 0 && ck + NST < nchunks) {
+        if (tid == 0 && q + NST < total) {
             ofr::fence_proxy_async();
-            issue(ck + NST, st);
+            issue(q + NST);
         }
-    }
-
-    const int y = y0 + row;
-    if (y < g.Hout) {
-        const long long ohw = (long long)g.Hout * g.Wout;
-        float* ob = out + ((long long)b * kD * kD + (long long)tjl * kD) * ohw + (long long)y * g.Wout;
-        const int xb = x0 + s * kM;
+        if (++ck == nchunks) {
+            // Tile finished.  Epilogue through shared memory and TMA stores: for each x-displacement j the CTA stages
+            // the 9 planes {tj*9 + j} (dense TH x TW boxes) and one thread issues 9 asynchronous tensor stores; the
+            // stores drain while the next tile is being computed, write whole 128-byte lines, and clip rows / columns
+            // outside the image by themselves.  Two staging buffers alternate.
+            int x0, y0, b;
+            tile_origin(tile_k, x0, y0, b);
+            const int rot = tj & 3;  // 16-byte chunk rotation: halves the bank conflicts of the 8 tj lanes of a quarter-warp
 #pragma unroll
-        for (int j = 0; j < kD; ++j) {
-            float* o = ob + (long long)j * ohw;
-            if (xb + kM <= g.Wout) {
-                ofr::stcs4(o + xb, make_float4(acc[0][j] * g.scale, acc[1][j] * g.scale, acc[2][j] * g.scale, acc[3][j] * g.scale));
-                ofr::stcs4(o + xb + 4, make_float4(acc[4][j] * g.scale, acc[5][j] * g.scale, acc[6][j] * g.scale, acc[7][j] * g.scale));
-            } else {
+            for (int j = 0; j < kD; ++j) {
+                float* buf = ostage + ((j + tile_k) & 1) * T::OS;  // 9 is odd: tile_k keeps consecutive groups alternating
+                if (tid == 0) ofr::tma_store_wait_read<1>();  // the group that last read this buffer is done with it
+                __syncthreads();
+                float* dst = buf + tj * T::OP + row * T::TW + s * M;
 #pragma unroll
-                for (int i = 0; i < kM; ++i)
-                    if (xb + i < g.Wout) o[xb + i] = acc[i][j] * g.scale;
+                for (int i0 = 0; i0 < M; i0 += 16) {
+                    float4 c[4];
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const int i = i0 + 4 * qd;
+                        c[qd] = (i < M) ? make_float4(acc[i % M][j] * g.scale, acc[(i + 1) % M][j] * g.scale,
+                                                      acc[(i + 2) % M][j] * g.scale, acc[(i + 3) % M][j] * g.scale)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (M >= 16) {
+                        // rotate the four chunks left by `rot` with selects (registers cannot be indexed dynamically)
+                        float4 d[4];
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const float4 p0 = c[qd], p1 = c[(qd + 1) & 3], p2 = c[(qd + 2) & 3], p3 = c[(qd + 3) & 3];
+                            d[qd] = rot == 0 ? p0 : rot == 1 ? p1 : rot == 2 ? p2 : p3;
+                        }
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            *reinterpret_cast<float4*>(dst + i0 + 4 * ((qd + rot) & 3)) = d[qd];
+                    } else {
+#pragma unroll
+                        for (int qd = 0; qd < M / 4; ++qd) *reinterpret_cast<float4*>(dst + i0 + 4 * qd) = c[qd];
+                    }
+                }
+                ofr::fence_proxy_async();  // make the generic-proxy writes visible to the TMA engine
+                __syncthreads();
+                if (tid == 0) {
+#pragma unroll
+                    for (int t = 0; t < kD; ++t) ofr::tma_store_4d(&mapO, buf + t * T::OP, x0, y0, t * kD + j, b);
+                    ofr::tma_store_commit();
+                }
             }
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int j = 0; j < kD; ++j) acc[i][j] = 0.f;
+            ck = 0;
+            ++tile_k;
         }
     }
+    if (tid == 0) ofr::tma_store_wait_all<0>();  // shared memory must outlive the stores that read it
 }
 
-template <int TH, int NS, int CK, int NST>
+template <int M, int TH, int NS, int CK, int NST>
 int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
-    using T = FwdT<TH, NS, CK, NST>;
-    CUtensorMap m1, m2;
-    if (!ofr::make_tmap_nchw(&m1, f1, g.B, g.C, g.H, g.W, T::TW, TH, CK)) return OFR_ENOTSUP;
+    using T = FwdT<M, TH, NS, CK, NST>;
+    CUtensorMap m1, m2, mo;
+    if (!ofr::make_tmap_nchw(&m1, f1, g.B, g.C, g.H, g.W, T::P1, TH, CK)) return OFR_ENOTSUP;
     if (!ofr::make_tmap_nchw(&m2, f2, g.B, g.C, g.H, g.W, T::P2, T::R2, CK)) return OFR_ENOTSUP;
-    auto kern = corr_fwd_tma_kernel<TH, NS, CK, NST>;
+    if (!ofr::make_tmap_nchw(&mo, out, g.B, kD * kD, g.Hout, g.Wout, T::TW, TH, 1)) return OFR_ENOTSUP;
+    auto kern = corr_fwd_tma_kernel<M, TH, NS, CK, NST>;
     OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
     const int tiles_x = (g.Wout + T::TW - 1) / T::TW, tiles_y = (g.Hout + TH - 1) / TH;
-    kern<<<(unsigned)(tiles_x * tiles_y * g.B), T::THREADS, T::SMEM, st>>>(m1, m2, out, g, tiles_x, tiles_y);
+    const long long ntiles = (long long)tiles_x * tiles_y * g.B;
+    const int ctas_per_sm = (int)(227 * 1024 / T::SMEM) < 1 ? 1 : (int)(227 * 1024 / T::SMEM);
+    long long grid = (long long)ofr::sm_count() * (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, T::THREADS, T::SMEM, st>>>(m1, m2, mo, g, tiles_x, tiles_y);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
@@ -327,10 +402,12 @@ namespace ofr {
 
 int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
     if (!applicable(g, f1, f2, out)) return OFR_ENOTSUP;
-    if (g.W > 32) return launch_fwd<8, 8, 8, 3>(f1, f2, out, g, st);   // 8 x 64 tile, 576 threads
-    if (g.W > 16) return launch_fwd<8, 4, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 288 threads
-    if (g.W > 8) return launch_fwd<8, 2, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile, 144 threads
-    return launch_fwd<4, 1, 8, 4>(f1, f2, out, g, st);                 // 4 x 8 tile,   36 threads
+    // 7 rows: 7 warps own tj = 0..7 and one warp owns tj = 8 -> 8 warps; a 9-warp CTA would be allocated registers
+    // for 12 warps and could not keep the 144 accumulators of the 16-pixel strip
+    if (g.W > 32) return launch_fwd<16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
+    if (g.W > 16) return launch_fwd<16, 8, 2, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads
+    if (g.W > 8) return launch_fwd<16, 8, 1, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile,  72 threads
+    return launch_fwd<8, 8, 1, 8, 4>(f1, f2, out, g, st);                  // 8 x 8 tile,   72 threads
 }
 
 int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,

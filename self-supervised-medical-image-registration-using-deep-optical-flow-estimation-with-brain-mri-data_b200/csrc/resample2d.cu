@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(32 * CG) resample_bwd_src_kernel(const float* 
     float ax = 0.f, ay = 0.f;
     if (in_range && s.live) {
         Taps<MODE> t(s, g);
+#pragma unroll 4
         for (int c = threadIdx.y; c < g.C; c += CG) {
             const float* img = in1 + ((long long)b * g.C + c) * hwi;
             const float go = __ldg(gO + ((long long)b * g.C + c) * hwf + rem);
@@ -493,54 +494,70 @@ __global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __re
 #pragma unroll
     for (int k = 0; k < kTgtChunk; ++k) acc[k] = 0.f;
 
-    // cells (ky, kx) in {ty-1, ty} x {tx-1, tx}; stored with a +1 bias
+    auto apply = [&](const int4 rec) {
+        const int src = rec.x;
+        Samp s;
+        unpack_xy(rec.y, s.x0, s.y0);
+        s.wx1 = __int_as_float(rec.z);
+        s.wy1 = __int_as_float(rec.w);
+        s.wx0 = __fsub_rn(1.f, s.wx1);
+        s.wy0 = __fsub_rn(1.f, s.wy1);
+        const Taps<MODE> t(s, g);
+        // weight of each of the four taps if it lands on this target, else 0 (order TL, TR, BL, BR)
+        const float w0 = (t.xl == tx && t.yt == ty) ? __fmul_rn(s.wx0, s.wy0) : 0.f;
+        const float w1 = (t.xr == tx && t.yt == ty) ? __fmul_rn(s.wx1, s.wy0) : 0.f;
+        const float w2 = (t.xl == tx && t.yb == ty) ? __fmul_rn(s.wx0, s.wy1) : 0.f;
+        const float w3 = (t.xr == tx && t.yb == ty) ? __fmul_rn(s.wx1, s.wy1) : 0.f;
+        float gv[kTgtChunk];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int ky = ty - 1 + (q >> 1), kx = tx - 1 + (q & 1);
-        const long long cell = cell_base + (long long)(ky + 1) * cw + (kx + 1);
-        const int n = counts[cell];
-        if (n == 0) continue;
-        const int4* e = entries + offsets[cell];
-        int last = -1;
-        for (int it = 0; it < n; ++it) {
-            int4 rec;
-            if (n == 1 || n > kHeavy) {
-                rec = __ldg(e + it);  // single entry, or pre-sorted by resample_sort_heavy_kernel
-            } else {                  // next entry in ascending source order
-                int best = 0x7fffffff, bj = 0;
-                for (int j = 0; j < n; ++j) {
-                    const int v = __ldg(&e[j].x);
-                    if (v > last && v < best) best = v, bj = j;
-                }
-                rec = __ldg(e + bj);
-                last = best;
-            }
-            const int src = rec.x;
-            Samp s;
-            unpack_xy(rec.y, s.x0, s.y0);
-            s.wx1 = __int_as_float(rec.z);
-            s.wy1 = __int_as_float(rec.w);
-            s.wx0 = __fsub_rn(1.f, s.wx1);
-            s.wy0 = __fsub_rn(1.f, s.wy1);
-            const Taps<MODE> t(s, g);
-            // weight of each of the four taps if it lands on this target, else 0 (order TL, TR, BL, BR)
-            const float w0 = (t.xl == tx && t.yt == ty) ? __fmul_rn(s.wx0, s.wy0) : 0.f;
-            const float w1 = (t.xr == tx && t.yt == ty) ? __fmul_rn(s.wx1, s.wy0) : 0.f;
-            const float w2 = (t.xl == tx && t.yb == ty) ? __fmul_rn(s.wx0, s.wy1) : 0.f;
-            const float w3 = (t.xr == tx && t.yb == ty) ? __fmul_rn(s.wx1, s.wy1) : 0.f;
+        for (int k = 0; k < kTgtChunk; ++k) gv[k] = (k < nc) ? __ldg(go + (long long)k * hwf + src) : 0.f;
 #pragma unroll
-            for (int k = 0; k < kTgtChunk; ++k) {
-                if (k < nc) {
-                    const float gv = __ldg(go + (long long)k * hwf + src);
-                    float a = acc[k];
-                    a = fmaf(w0, gv, a);
-                    a = fmaf(w1, gv, a);
-                    a = fmaf(w2, gv, a);
-                    a = fmaf(w3, gv, a);
-                    acc[k] = a;
-                }
-            }
+        for (int k = 0; k < kTgtChunk; ++k) {
+            float a = acc[k];
+            a = fmaf(w0, gv[k], a);
+            a = fmaf(w1, gv[k], a);
+            a = fmaf(w2, gv[k], a);
+            a = fmaf(w3, gv[k], a);
+            acc[k] = a;
         }
+    };
+
+    // cells (ky, kx) in {ty-1, ty} x {tx-1, tx}, stored with a +1 bias: indices base0 + {0, 1, cw, cw+1}.
+    // All count / offset loads are issued together (one round trip).  The records are then visited by ONE loop with
+    // ONE `apply` site -- cell after cell, ascending source index inside a cell -- so the lanes of a warp stay
+    // converged however differently their cells are filled.
+    const long long base0 = cell_base + (long long)ty * cw + tx;
+    const int n0 = __ldg(counts + base0), n1 = __ldg(counts + base0 + 1);
+    const int n2 = __ldg(counts + base0 + cw), n3 = __ldg(counts + base0 + cw + 1);
+    const int4* e0 = entries + __ldg(offsets + base0);
+    const int4* e1 = entries + __ldg(offsets + base0 + 1);
+    const int4* e2 = entries + __ldg(offsets + base0 + cw);
+    const int4* e3 = entries + __ldg(offsets + base0 + cw + 1);
+    int q = 0, it = 0, last = -1;
+    while (true) {
+        int n = q == 0 ? n0 : q == 1 ? n1 : q == 2 ? n2 : n3;
+        while (q < 4 && it >= n) {
+            ++q;
+            it = 0;
+            last = -1;
+            n = q == 1 ? n1 : q == 2 ? n2 : n3;
+        }
+        if (q >= 4) break;
+        const int4* e = q == 0 ? e0 : q == 1 ? e1 : q == 2 ? e2 : e3;
+        int4 rec;
+        if (n == 1 || n > kHeavy) {  // single entry, or pre-sorted by resample_sort_heavy_kernel
+            rec = __ldg(e + it);
+        } else {  // next entry in ascending source order
+            int best = 0x7fffffff, bj = 0;
+            for (int j = 0; j < n; ++j) {
+                const int v = __ldg(&e[j].x);
+                if (v > last && v < best) best = v, bj = j;
+            }
+            rec = __ldg(e + bj);
+            last = best;
+        }
+        ++it;
+        apply(rec);
     }
 #pragma unroll
     for (int k = 0; k < kTgtChunk; ++k)

@@ -304,3 +304,38 @@ def test_loss_degenerate_and_reproducible(ofr, golden):
     a = ofr.OFEloss(flows, warps, fixed)
     b = ofr.OFEloss(flows, warps, fixed)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+# =============================================================================== model level
+def test_pwcnet_training_step_matches_oracle_layers(ofr):
+    """The whole hot path in situ: host PWC-Net + stn warps + OFEloss, CUDA layers on the GPU against the same model
+    with every hot-path layer served by the CPU oracle (same weights, same input)."""
+    from ofr_b200.harness import PWCNetHost, RegistrationStep, synthetic_pairs
+
+    class OracleCorrelation(torch.nn.Module):
+        def forward(self, a, b):
+            return oracle.correlation(a, b, 4, 1, 4, 1, 1)
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # float32 convolutions on both sides
+    try:
+        torch.manual_seed(6)
+        cpu_host = PWCNetHost(md=4, corr=OracleCorrelation(), warp=oracle.pwc_warp)
+        gpu_host = PWCNetHost(md=4).to(DEV)
+        gpu_host.load_state_dict(cpu_host.state_dict())
+        cpu_step = RegistrationStep(cpu_host, oracle.stn_warp, oracle.ofe_loss)
+        gpu_step = RegistrationStep(gpu_host, ofr.stn_warp, ofr.OFEloss)
+        pair = synthetic_pairs(2, 128, seed=6)
+        ref = cpu_step(pair)
+        got = gpu_step(pair.to(DEV))
+        for r, g_ in zip(ref, got):
+            assert abs(g_.item() - r.item()) <= 2e-3 * abs(r.item()) + 1e-6, (g_.item(), r.item())
+        ref[3].backward()
+        got[3].backward()
+        for name in ["conv6b.0.weight", "conv2_0.0.weight", "predict_flow2.weight", "conv1a.0.weight"]:
+            a = dict(gpu_host.named_parameters())[name].grad.cpu().double()
+            b = dict(cpu_host.named_parameters())[name].grad.double()
+            rel = (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+            assert rel < 2e-2, (name, rel)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -1,0 +1,124 @@
+"""CPU: the measurement harness (host model, synthetic data, training step, data-parallel sharding).
+
+The harness takes its hot-path layers by injection; here they are the CPU oracle, so the host-side logic
+(model wiring, step, DDP gradient averaging over gloo with world_size 2) is covered without a GPU.
+"""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+
+REF = "/root/reference"
+
+
+class OracleCorrelation(torch.nn.Module):
+    def forward(self, a, b):
+        return oracle.correlation(a, b, 4, 1, 4, 1, 1)
+
+
+def make_step(seed=6):
+    from ofr_b200.harness import PWCNetHost, RegistrationStep
+    torch.manual_seed(seed)
+    host = PWCNetHost(md=4, corr=OracleCorrelation(), warp=oracle.pwc_warp)
+    host.deconv0.requires_grad_(False)
+    return RegistrationStep(host, oracle.stn_warp, oracle.ofe_loss)
+
+
+def test_host_model_shapes_and_parameter_count():
+    step = make_step()
+    assert sum(p.numel() for p in step.predictor.parameters()) == 9374184
+    assert len(step.predictor.state_dict()) == len(list(step.predictor.parameters()))  # no buffers
+    x = torch.rand(1, 2, 64, 64)
+    with torch.no_grad():
+        flows = step.predictor(x)
+    assert [tuple(f.shape) for f in flows] == [(1, 2, s, s) for s in (64, 32, 16, 8, 4, 2, 1)]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
+def test_host_model_equals_reference_class():
+    """Same state_dict keys/shapes as PWC/models/PWCNet.py:38-135 and bitwise-equal outputs with shared weights."""
+    import ofr_b200
+    ofr_b200.install_shims()
+    sys.path.insert(0, os.path.join(REF, "PWC", "models"))
+    real_cuda = torch.Tensor.cuda
+    try:
+        import PWCNet
+        ref = PWCNet.PWCDCNet(md=4)
+        ref.corr = OracleCorrelation()
+        host = make_step().predictor
+        sd = ref.state_dict()
+        assert set(sd) == set(host.state_dict())
+        host.load_state_dict(sd)
+        torch.Tensor.cuda = lambda self, *a, **k: self  # PWCNet.py:169 moves the mask unconditionally
+        x = torch.rand(1, 2, 64, 64, generator=torch.Generator().manual_seed(1))
+        with torch.no_grad():
+            a, b = ref(x), host(x)
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+    finally:
+        torch.Tensor.cuda = real_cuda
+        sys.path.remove(os.path.join(REF, "PWC", "models"))
+        sys.modules.pop("PWCNet", None)
+        ofr_b200.uninstall_shims()
+
+
+def test_synthetic_pairs_are_deterministic_and_normalised():
+    from ofr_b200.harness import synthetic_pairs
+    a, b = synthetic_pairs(2, 64, seed=6), synthetic_pairs(2, 64, seed=6)
+    assert torch.equal(a, b) and a.shape == (2, 2, 64, 64)
+    assert float(a[:, 0].amin()) == 0.0 and abs(float(a[:, 0].amax()) - 1.0) < 1e-6
+    assert not torch.equal(a, synthetic_pairs(2, 64, seed=7))
+    assert float((a[:, 0] - a[:, 1]).abs().mean()) > 1e-3  # moving really is deformed
+
+
+def test_training_step_reduces_loss():
+    from ofr_b200.harness import synthetic_pairs, make_optimizer, train_step
+    step = make_step()
+    opt = make_optimizer(step.predictor, lr=1e-4)
+    pair = synthetic_pairs(1, 64, seed=6)
+    losses = [float(train_step(step, opt, pair)) for _ in range(3)]
+    assert all(l == l and l > 0 for l in losses)
+    assert losses[-1] < losses[0]
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ofr_b200.harness import synthetic_pairs
+        torch.set_num_threads(2)
+        step = make_step(seed=6)  # identical weights on every rank
+        local = make_step(seed=6)
+        step.predictor = torch.nn.parallel.DistributedDataParallel(step.predictor)
+        pair = synthetic_pairs(1, 64, seed=10 + rank)  # rank-offset data shard
+        step(pair)[3].backward()
+        local(pair)[3].backward()
+        mine = torch.cat([p.grad.flatten() for p in local.predictor.parameters() if p.grad is not None]).double()
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        expect = sum(gathered) / world  # DDP averages the per-shard gradients
+        got = torch.cat([p.grad.flatten() for p in step.predictor.parameters() if p.grad is not None]).double()
+        q.put((rank, float((got - expect).abs().max()), float(expect.abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_gloo_world2_averages_shard_gradients():
+    """Batch sharding needs no collective inside the layers: one all-reduce of the gradients per step."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    res = [q.get(timeout=10) for _ in range(2)]
+    for rank, err, scale in res:
+        assert err <= 1e-5 * max(scale, 1.0), (rank, err, scale)
