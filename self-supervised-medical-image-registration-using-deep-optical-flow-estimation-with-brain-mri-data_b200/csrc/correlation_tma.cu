@@ -243,7 +243,8 @@ struct BwdT {
     static constexpr int FT = kCB * R2 * P2;      // resident feature tile, floats
     // TMA needs a 16-byte aligned box origin along x, so the shifted planes of the second gradient are staged as
     // aligned boxes widened by the halo and the +-4 pixel shift is applied when the registers are filled.
-    static constexpr int GW = SHIFTED ? TW + 2 * kR : TW;  // row pitch of a staged gradient plane
+    // row pitch of a staged gradient plane: 4*odd (mod 32) floats, so the 8 rows read by a quarter-warp hit 8 bank groups
+    static constexpr int GW = pitch_for(SHIFTED ? TW + 2 * kR : TW);
     static constexpr int GP = kBTH * GW;                    // one plane tile, floats
     static constexpr int GS = kD * GP;                      // one gradient stage (9 planes), floats
     static constexpr int THREADS = kBTH * NS * kCG;
@@ -271,10 +272,12 @@ __global__ void __launch_bounds__(BwdT<NS, SHIFTED>::THREADS, 1)
     const int b = bid / cblocks;
     const int x0 = txi * T::TW, y0 = tyi * kBTH, c0 = cbi * kCB;
 
+    // lanes: 8 rows (fastest) x 4 channel groups of ONE strip -> a quarter-warp reads 8 different rows of the feature /
+    // gradient tiles, whose pitches are 4*odd (mod 32): conflict-free 128-bit LDS
     const int tid = threadIdx.x;
-    const int cg = tid % kCG;
-    const int s = (tid / kCG) % NS;
-    const int row = tid / (kCG * NS);
+    const int row = tid % kBTH;
+    const int cg = (tid / kBTH) % kCG;
+    const int s = tid / (kBTH * kCG);
 
     auto issue_g = [&](int tji, int st) {
         float* dst = Gs + st * T::GS;

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(32 * CG) resample_bwd_src_kernel(const float* 
     float ax = 0.f, ay = 0.f;
     if (in_range && s.live) {
         Taps<MODE> t(s, g);
-#pragma unroll 4
+#pragma unroll 8
         for (int c = threadIdx.y; c < g.C; c += CG) {
             const float* img = in1 + ((long long)b * g.C + c) * hwi;
             const float go = __ldg(gO + ((long long)b * g.C + c) * hwf + rem);
@@ -437,6 +437,39 @@ __global__ void __launch_bounds__(256) resample_fill_kernel(const float* __restr
     if (r == 0 && counts[cell] > kHeavy) heavy[atomicAdd(heavy_n, 1)] = cell;
 }
 
+// ---- sort the records of every cell with 2..kHeavy entries by source index (ascending): one thread per cell,
+// insertion sort on a private copy.  After this pass and the heavy pass every cell is in canonical order, so the
+// per-target gather streams its records without any searching.
+__global__ void __launch_bounds__(128) resample_sort_small_kernel(const int* __restrict__ counts,
+                                                                  const int* __restrict__ offsets,
+                                                                  int4* __restrict__ entries, int ncell) {
+    const int cell = blockIdx.x * 128 + threadIdx.x;
+    if (cell >= ncell) return;
+    const int n = counts[cell];
+    if (n < 2 || n > kHeavy) return;
+    int4* a = entries + offsets[cell];
+    if (n == 2) {  // by far the most common crowded cell
+        const int4 r0 = a[0], r1 = a[1];
+        if (r0.x > r1.x) {
+            a[0] = r1;
+            a[1] = r0;
+        }
+        return;
+    }
+    int4 v[kHeavy];
+    for (int i = 0; i < n; ++i) v[i] = a[i];
+    for (int i = 1; i < n; ++i) {
+        const int4 key = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j].x > key.x) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = key;
+    }
+    for (int i = 0; i < n; ++i) a[i] = v[i];
+}
+
 // ---- sort the entries of crowded cells (ascending).  One CTA per heavy cell, all-ascending bitonic
 // network ("flip" first step) so a virtual +inf padding beyond n never has to move.
 __global__ void __launch_bounds__(512) resample_sort_heavy_kernel(const int* __restrict__ heavy,
@@ -469,33 +502,98 @@ __global__ void __launch_bounds__(512) resample_sort_heavy_kernel(const int* __r
     }
 }
 
-// ---- per-target gather of the adjoint.  Thread = one target pixel, blockIdx.y = channel chunk.
-constexpr int kTgtChunk = 16;
+// ---- per-target gather of the adjoint, one CTA per tile of targets.
+// A CTA owns kTY x kTX targets of one image and ALL channels.  The records that can reach the tile live in the
+// (kTY+1) x (kTX+1) block of cells around it; each row of that block is one contiguous run of the CSR, so the CTA
+// copies the runs into shared memory with coalesced 16-byte loads ONCE and every thread then walks its <= 4 cells
+// out of shared memory (no dependent global round trips), channel chunk after channel chunk.  Only the gradient
+// gathers go to global memory; lanes are consecutive targets, so for smooth flows they coalesce.
+// Visiting order per target: cell (ty-1,tx-1), (ty-1,tx), (ty,tx-1), (ty,tx), ascending source index inside a cell
+// (the cells were sorted by resample_sort_small/heavy_kernel) -- a function of the data only: bitwise reproducible.
+constexpr int kTY = 8, kTX = 32, kTgtThreads = kTY * kTX;
+constexpr int kTgtChunk = 16;      // channels accumulated per sweep over a thread's records
+constexpr int kRecCap = 1024;      // records staged per tile (16 KB); denser tiles read their records from global
+constexpr int kListCap = 8;        // decoded (source, weight) pairs kept per target (16 KB per CTA)
 
 template <int MODE>
-__global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __restrict__ gO,
-                                                               const int* __restrict__ counts,
-                                                               const int* __restrict__ offsets,
-                                                               const int4* __restrict__ entries,
-                                                               float* __restrict__ gI1, WarpGeom g) {
+__global__ void __launch_bounds__(kTgtThreads, 4) resample_bwd_tgt_kernel(const float* __restrict__ gO,
+                                                                       const int* __restrict__ counts,
+                                                                       const int* __restrict__ offsets,
+                                                                       const int4* __restrict__ entries,
+                                                                       float* __restrict__ gI1, WarpGeom g,
+                                                                       int tiles_x, int tiles_y, int chunks_per_cta) {
+    __shared__ int4 srec[kRecCap];
+    __shared__ int2 elist[kListCap][kTgtThreads];
+    __shared__ int soff[kTY + 1][kTX + 2];  // CSR offset of every cell of the block (+1 column: end of the run)
+    __shared__ int spos[kTY + 2];           // where the run of each cell row starts in srec
+
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x;
+    bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int tx0 = txi * kTX, ty0 = tyi * kTY;
+    const int cw = g.Win + 1, ch = g.Hin + 1;
+    const long long cell_base = (long long)b * ch * cw;
     const long long hwf = (long long)g.Hf * g.Wf, hwi = (long long)g.Hin * g.Win;
-    const long long tpix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (tpix >= (long long)g.B * hwi) return;
-    const int b = (int)(tpix / hwi);
-    const int trem = (int)(tpix - (long long)b * hwi);
-    const int ty = trem / g.Win, tx = trem - ty * g.Win;
-    const int c0 = blockIdx.y * kTgtChunk;
-    const int nc = min(kTgtChunk, g.C - c0);
-    const int cw = g.Win + 1;
-    const long long cell_base = (long long)b * (g.Hin + 1) * cw;
-    const float* go = gO + ((long long)b * g.C + c0) * hwf;
 
-    float acc[kTgtChunk];
+    // biased cell coordinates of the block: rows ty0 .. ty0+kTY, columns tx0 .. tx0+kTX  (cell (ky,kx) is stored at
+    // (ky+1, kx+1), and target (ty,tx) reads cells (ty-1..ty, tx-1..tx))
+    for (int i = threadIdx.x; i < (kTY + 1) * (kTX + 2); i += kTgtThreads) {
+        const int r = i / (kTX + 2), c = i - r * (kTX + 2);
+        const int cy = ty0 + r, cx = tx0 + c;
+        int v = 0;
+        // one past the last cell of a row is the first cell of the next row (or offsets[ncell] = total): same array
+        if (cy < ch) v = __ldg(offsets + cell_base + (long long)cy * cw + min(cx, cw));
+        soff[r][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int at = 0;
+        for (int r = 0; r <= kTY; ++r) {
+            spos[r] = at;
+            const int cy = ty0 + r;
+            if (cy < ch) {
+                const int cend = min(kTX + 1, cw - tx0);  // first column index after the block (clipped to the row)
+                at += soff[r][cend] - soff[r][0];
+            }
+        }
+        spos[kTY + 1] = at;
+    }
+    __syncthreads();
+    const int total = spos[kTY + 1];
+    const bool staged = total <= kRecCap;
+    if (staged) {
+        for (int r = 0; r <= kTY; ++r) {
+            const int n = spos[r + 1] - spos[r];
+            const int4* src = entries + soff[r][0];
+            for (int i = threadIdx.x; i < n; i += kTgtThreads) srec[spos[r] + i] = __ldg(src + i);
+        }
+    }
+    __syncthreads();
+
+    const int lx = threadIdx.x % kTX, ly = threadIdx.x / kTX;
+    const int tx = tx0 + lx, ty = ty0 + ly;
+    const bool live = tx < g.Win && ty < g.Hin;
+    // the four cells of this target: block rows ly, ly+1 ; block columns lx, lx+1
+    int start[4], cnt[4];
 #pragma unroll
-    for (int k = 0; k < kTgtChunk; ++k) acc[k] = 0.f;
+    for (int q = 0; q < 4; ++q) {
+        const int r = ly + (q >> 1), c = lx + (q & 1);
+        const bool in = live && (ty0 + r) < ch && (tx0 + c) < cw;
+        const int o = soff[r][c];
+        cnt[q] = in ? soff[r][c + 1] - o : 0;
+        start[q] = staged ? spos[r] + (o - soff[r][0]) : o;
+    }
+    const int s1 = cnt[0], s2 = s1 + cnt[1], s3 = s2 + cnt[2], tot = s3 + cnt[3];
+    const int trem = ty * g.Win + tx;
 
-    auto apply = [&](const int4 rec) {
-        const int src = rec.x;
+    // e-th record of this target in visiting order -> (source index, weight).  The weight is the sum, in tap order
+    // TL, TR, BL, BR, of the taps of that source that land on this target (exactly one away from clamped borders).
+    auto entry = [&](int e, int& src, float& w) {
+        const int q = (e >= s1) + (e >= s2) + (e >= s3);  // no dynamically indexed arrays
+        const int base = q == 0 ? start[0] : q == 1 ? start[1] - s1 : q == 2 ? start[2] - s2 : start[3] - s3;
+        const int4 rec = staged ? srec[base + e] : __ldg(entries + base + e);
         Samp s;
         unpack_xy(rec.y, s.x0, s.y0);
         s.wx1 = __int_as_float(rec.z);
@@ -503,65 +601,60 @@ __global__ void __launch_bounds__(128) resample_bwd_tgt_kernel(const float* __re
         s.wx0 = __fsub_rn(1.f, s.wx1);
         s.wy0 = __fsub_rn(1.f, s.wy1);
         const Taps<MODE> t(s, g);
-        // weight of each of the four taps if it lands on this target, else 0 (order TL, TR, BL, BR)
-        const float w0 = (t.xl == tx && t.yt == ty) ? __fmul_rn(s.wx0, s.wy0) : 0.f;
-        const float w1 = (t.xr == tx && t.yt == ty) ? __fmul_rn(s.wx1, s.wy0) : 0.f;
-        const float w2 = (t.xl == tx && t.yb == ty) ? __fmul_rn(s.wx0, s.wy1) : 0.f;
-        const float w3 = (t.xr == tx && t.yb == ty) ? __fmul_rn(s.wx1, s.wy1) : 0.f;
-        float gv[kTgtChunk];
-#pragma unroll
-        for (int k = 0; k < kTgtChunk; ++k) gv[k] = (k < nc) ? __ldg(go + (long long)k * hwf + src) : 0.f;
-#pragma unroll
-        for (int k = 0; k < kTgtChunk; ++k) {
-            float a = acc[k];
-            a = fmaf(w0, gv[k], a);
-            a = fmaf(w1, gv[k], a);
-            a = fmaf(w2, gv[k], a);
-            a = fmaf(w3, gv[k], a);
-            acc[k] = a;
-        }
+        float acc = 0.f;
+        if (t.xl == tx && t.yt == ty) acc = __fadd_rn(acc, __fmul_rn(s.wx0, s.wy0));
+        if (t.xr == tx && t.yt == ty) acc = __fadd_rn(acc, __fmul_rn(s.wx1, s.wy0));
+        if (t.xl == tx && t.yb == ty) acc = __fadd_rn(acc, __fmul_rn(s.wx0, s.wy1));
+        if (t.xr == tx && t.yb == ty) acc = __fadd_rn(acc, __fmul_rn(s.wx1, s.wy1));
+        src = rec.x;
+        w = acc;
     };
-
-    // cells (ky, kx) in {ty-1, ty} x {tx-1, tx}, stored with a +1 bias: indices base0 + {0, 1, cw, cw+1}.
-    // All count / offset loads are issued together (one round trip).  The records are then visited by ONE loop with
-    // ONE `apply` site -- cell after cell, ascending source index inside a cell -- so the lanes of a warp stay
-    // converged however differently their cells are filled.
-    const long long base0 = cell_base + (long long)ty * cw + tx;
-    const int n0 = __ldg(counts + base0), n1 = __ldg(counts + base0 + 1);
-    const int n2 = __ldg(counts + base0 + cw), n3 = __ldg(counts + base0 + cw + 1);
-    const int4* e0 = entries + __ldg(offsets + base0);
-    const int4* e1 = entries + __ldg(offsets + base0 + 1);
-    const int4* e2 = entries + __ldg(offsets + base0 + cw);
-    const int4* e3 = entries + __ldg(offsets + base0 + cw + 1);
-    int q = 0, it = 0, last = -1;
-    while (true) {
-        int n = q == 0 ? n0 : q == 1 ? n1 : q == 2 ? n2 : n3;
-        while (q < 4 && it >= n) {
-            ++q;
-            it = 0;
-            last = -1;
-            n = q == 1 ? n1 : q == 2 ? n2 : n3;
-        }
-        if (q >= 4) break;
-        const int4* e = q == 0 ? e0 : q == 1 ? e1 : q == 2 ? e2 : e3;
-        int4 rec;
-        if (n == 1 || n > kHeavy) {  // single entry, or pre-sorted by resample_sort_heavy_kernel
-            rec = __ldg(e + it);
-        } else {  // next entry in ascending source order
-            int best = 0x7fffffff, bj = 0;
-            for (int j = 0; j < n; ++j) {
-                const int v = __ldg(&e[j].x);
-                if (v > last && v < best) best = v, bj = j;
-            }
-            rec = __ldg(e + bj);
-            last = best;
-        }
-        ++it;
-        apply(rec);
+    // decode the first kListCap records once; the channel sweeps below then only do gather + FMA
+    const int nlist = min(tot, kListCap);
+    for (int e = 0; e < nlist; ++e) {
+        int src;
+        float w;
+        entry(e, src, w);
+        elist[e][threadIdx.x] = make_int2(src, __float_as_int(w));
     }
+    // (each thread reads back only what it wrote itself: no barrier needed)
+
+    const int cbeg = blockIdx.y * chunks_per_cta * kTgtChunk;
+    const int cend = min(g.C, cbeg + chunks_per_cta * kTgtChunk);
+    for (int c0 = cbeg; c0 < cend; c0 += kTgtChunk) {
+        const int nc = min(kTgtChunk, g.C - c0);
+        const float* go = gO + ((long long)b * g.C + c0) * hwf;
+        float acc[kTgtChunk];
 #pragma unroll
-    for (int k = 0; k < kTgtChunk; ++k)
-        if (k < nc) gI1[((long long)b * g.C + c0 + k) * hwi + trem] = acc[k];
+        for (int k = 0; k < kTgtChunk; ++k) acc[k] = 0.f;
+        for (int e = 0; e < tot; ++e) {
+            int src;
+            float w;
+            if (e < kListCap) {
+                const int2 v = elist[e][threadIdx.x];
+                src = v.x;
+                w = __int_as_float(v.y);
+            } else {
+                entry(e, src, w);  // crowded targets (> kListCap records): decode on the fly
+            }
+            const float* gp = go + src;
+            float gv[kTgtChunk];
+            if (nc == kTgtChunk) {  // full chunk: no per-channel predicates
+#pragma unroll
+                for (int k = 0; k < kTgtChunk; ++k) gv[k] = __ldg(gp + (size_t)k * (size_t)hwf);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kTgtChunk; ++k) gv[k] = (k < nc) ? __ldg(gp + (size_t)k * (size_t)hwf) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < kTgtChunk; ++k) acc[k] = fmaf(w, gv[k], acc[k]);
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < kTgtChunk; ++k)
+                if (k < nc) gI1[((long long)b * g.C + c0 + k) * hwi + trem] = acc[k];
+        }
+    }
 }
 
 // nearest mode: the flow gets no gradient; the image gradient is still a (deterministic) gather,
@@ -577,16 +670,16 @@ WsLayout ws_layout(int B, int Hin, int Win, int Hf, int Wf) {
     WsLayout L;
     L.ncell = B * (Hin + 1) * (Win + 1);
     L.npix = (long long)B * Hf * Wf;
-    L.nblk = (L.ncell + kScanTile - 1) / kScanTile;
+    L.nblk = (L.ncell + 1 + kScanTile - 1) / kScanTile;  // the scan runs over ncell+1 items: offsets[ncell] = total
     size_t o = 0;
     auto take = [&](size_t bytes) {
         size_t at = o;
         o = ofr::align_up(o + bytes, 256);
         return at;
     };
-    L.counts = take(sizeof(int) * (size_t)L.ncell);
+    L.counts = take(sizeof(int) * ((size_t)L.ncell + 1));
     L.misc = take(256);
-    L.offsets = take(sizeof(int) * (size_t)L.ncell);
+    L.offsets = take(sizeof(int) * ((size_t)L.ncell + 1));
     L.blocksum = take(sizeof(int) * (size_t)L.nblk);
     L.key = take(sizeof(int) * (size_t)L.npix);
     L.rank = take(sizeof(int) * (size_t)L.npix);
@@ -682,26 +775,47 @@ int run_bwd(const float* in1, const float* flow, const float* gO, float* gI1, fl
         else
             resample_bwd_src4_kernel<MODE, false, true><<<grid, 256, 0, st>>>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy);
         rc = ofr::after_launch();
-    } else if (g.C >= 8)
-        rc = launch_src<MODE, 8>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
-    else
-        rc = launch_src<MODE, 1>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+    } else {
+        // Channel split across the CTA only as far as needed to fill the machine: this kernel is a chain of dependent
+        // memory round trips, so its time is (warps / resident warps) x chain latency -- fewer, longer-running warps
+        // with more independent loads each are better than many short ones once the SMs are full.
+        const long long pix_warps = ((long long)g.B * g.Hf * g.Wf + 31) / 32;
+        const long long want = 6ll * 32 * ofr::sm_count();  // ~6 waves of 32 resident warps per SM
+        if (g.C >= 8 && pix_warps * 4 < want)
+            rc = launch_src<MODE, 8>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+        else if (g.C >= 4 && pix_warps * 2 < want)
+            rc = launch_src<MODE, 4>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+        else if (g.C >= 2 && pix_warps < want)
+            rc = launch_src<MODE, 2>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+        else
+            rc = launch_src<MODE, 1>(in1, flow, gO, gI2, counts, key, rank, g, sx, sy, want_bin, st);
+    }
     if (rc != OFR_OK || !want_bin) return rc;
 
-    scan_reduce_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, L.ncell);
+    scan_reduce_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, L.ncell + 1);
     OFR_LAUNCH_CHECK();
     scan_top_kernel<<<1, 1024, 0, st>>>(blocksum, L.nblk);
     OFR_LAUNCH_CHECK();
-    scan_apply_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, offsets, L.ncell);
+    scan_apply_kernel<<<L.nblk, kScanThreads, 0, st>>>(counts, blocksum, offsets, L.ncell + 1);
     OFR_LAUNCH_CHECK();
     resample_fill_kernel<MODE><<<(unsigned)((L.npix + 255) / 256), 256, 0, st>>>(flow, key, rank, counts, offsets,
                                                                                 entries, heavy, misc, g);
     OFR_LAUNCH_CHECK();
+    resample_sort_small_kernel<<<(unsigned)((L.ncell + 127) / 128), 128, 0, st>>>(counts, offsets, entries, L.ncell);
+    OFR_LAUNCH_CHECK();
     resample_sort_heavy_kernel<<<ofr::sm_count(), 512, 0, st>>>(heavy, misc, counts, offsets, entries);
     OFR_LAUNCH_CHECK();
-    const long long ntgt = (long long)g.B * g.Hin * g.Win;
-    dim3 grid((unsigned)((ntgt + 127) / 128), (unsigned)((g.C + kTgtChunk - 1) / kTgtChunk));
-    resample_bwd_tgt_kernel<MODE><<<grid, 128, 0, st>>>(gO, counts, offsets, entries, gI1, g);
+    const int tiles_x = (g.Win + kTX - 1) / kTX, tiles_y = (g.Hin + kTY - 1) / kTY;
+    // all channels in one CTA when there are enough tiles to fill the GPU; otherwise split the channel chunks over
+    // blockIdx.y (each CTA re-stages the tile's records, which is cheap)
+    const int nchunks = (g.C + kTgtChunk - 1) / kTgtChunk;
+    const long long ntile = (long long)tiles_x * tiles_y * g.B;
+    int split = (int)((4ll * ofr::sm_count() + ntile - 1) / ntile);
+    split = split < 1 ? 1 : (split > nchunks ? nchunks : split);
+    const int chunks_per_cta = (nchunks + split - 1) / split;
+    dim3 grid((unsigned)ntile, (unsigned)((nchunks + chunks_per_cta - 1) / chunks_per_cta));
+    resample_bwd_tgt_kernel<MODE><<<grid, kTgtThreads, 0, st>>>(gO, counts, offsets, entries, gI1, g, tiles_x, tiles_y,
+                                                                chunks_per_cta);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }

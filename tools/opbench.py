@@ -54,7 +54,9 @@ def cases(B, S):
 
     def warp(tag, C, h, mode, want1, sigma):
         x = torch.randn(B, C, h, h, device=DEV)
-        fl = torch.randn(B, 2, h, h, device=DEV) * sigma
+        # smooth flow (coarse random field upsampled 8x), like the decoder's upsampled flows -- not white noise
+        fl = torch.nn.functional.interpolate(torch.randn(B, 2, max(h // 8, 1), max(h // 8, 1), device=DEV) * sigma,
+                                             size=(h, h), mode="bilinear", align_corners=False).contiguous()
         o = torch.empty_like(x)
         go = torch.randn_like(x)
         g1 = torch.empty_like(x) if want1 else None
