@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define OFR_ABI_VERSION 1
+#define OFR_ABI_VERSION 2
 
 typedef void* ofr_stream_t; /* cudaStream_t */
 
@@ -67,14 +67,21 @@ uint64_t ofr_launch_count(void);
  */
 int ofr_corr_out_shape(int H, int W, int pad, int k, int md, int s1, int s2,
                        int* D, int* Hout, int* Wout);
+/* Bytes of scratch the fast path of this geometry wants (0 = none).  backward != 0 sizes the backward call.
+ * The stride2 = 2 configuration (FlowNetC) runs as four stride-1 correlations on the 2x2 polyphase components of
+ * the inputs and needs room for the split copies.  Passing ws = NULL (or too little) is legal: the call then takes a
+ * slower kernel that needs no scratch. */
+size_t ofr_corr_workspace(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2, int backward);
 int ofr_corr_fwd(const float* f1, const float* f2, float* out,
                  int B, int C, int H, int W,
-                 int pad, int k, int md, int s1, int s2, ofr_stream_t stream);
+                 int pad, int k, int md, int s1, int s2,
+                 void* ws, size_t ws_bytes, ofr_stream_t stream);
 /* gI1 / gI2 may each be NULL to skip that gradient. */
 int ofr_corr_bwd(const float* f1, const float* f2, const float* gO,
                  float* gI1, float* gI2,
                  int B, int C, int H, int W,
-                 int pad, int k, int md, int s1, int s2, ofr_stream_t stream);
+                 int pad, int k, int md, int s1, int s2,
+                 void* ws, size_t ws_bytes, ofr_stream_t stream);
 
 /* ------------------------------------------------------------------ Resample / warps
  * One kernel family, three sampling conventions:

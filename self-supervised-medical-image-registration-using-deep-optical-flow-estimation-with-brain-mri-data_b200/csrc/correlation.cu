@@ -307,6 +307,80 @@ int launch_tiled(const float* f1, const float* f2, float* out, const CorrGeom& g
     return OFR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ polyphase split
+// stride2 = 2 (FlowNetC): pixel (y,x) only meets f2 pixels (y + 2tj, x + 2ti) of its own parity class, so the operator
+// factors into four independent stride-1 correlations (R = md/2) on the class images [B][4][C][H/2][W/2].  The split /
+// merge passes are pure streaming copies (128-bit loads, 64-bit stores) and cost a few percent of the FMA-bound
+// correlation they enable; they replace upstream's NHWC repack of both inputs.
+__global__ void __launch_bounds__(256) polyphase_split_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int B, int C, int H, int W) {
+    const int w4 = W / 4, h2 = H / 2, w2 = W / 2;
+    const long long total = (long long)B * C * H * w4;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        long long t = i;
+        const int q = (int)(t % w4);
+        t /= w4;
+        const int y = (int)(t % H);
+        t /= H;
+        const int c = (int)(t % C);
+        const int b = (int)(t / C);
+        const float4 v = ofr::ldg4(src + (((long long)b * C + c) * H + y) * W + 4 * q);
+        const int py = y & 1;
+        float* d0 = dst + ((((long long)b * 4 + py * 2 + 0) * C + c) * h2 + (y >> 1)) * w2 + 2 * q;
+        float* d1 = dst + ((((long long)b * 4 + py * 2 + 1) * C + c) * h2 + (y >> 1)) * w2 + 2 * q;
+        *reinterpret_cast<float2*>(d0) = make_float2(v.x, v.z);
+        *reinterpret_cast<float2*>(d1) = make_float2(v.y, v.w);
+    }
+}
+
+__global__ void __launch_bounds__(256) polyphase_merge_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int B, int C, int H, int W) {
+    const int w4 = W / 4, h2 = H / 2, w2 = W / 2;
+    const long long total = (long long)B * C * H * w4;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        long long t = i;
+        const int q = (int)(t % w4);
+        t /= w4;
+        const int y = (int)(t % H);
+        t /= H;
+        const int c = (int)(t % C);
+        const int b = (int)(t / C);
+        const int py = y & 1;
+        const float2 e = __ldg(reinterpret_cast<const float2*>(
+            src + ((((long long)b * 4 + py * 2 + 0) * C + c) * h2 + (y >> 1)) * w2 + 2 * q));
+        const float2 o = __ldg(reinterpret_cast<const float2*>(
+            src + ((((long long)b * 4 + py * 2 + 1) * C + c) * h2 + (y >> 1)) * w2 + 2 * q));
+        ofr::stcs4(dst + (((long long)b * C + c) * H + y) * W + 4 * q, make_float4(e.x, o.x, e.y, o.y));
+    }
+}
+
+int polyphase(bool split, const float* src, float* dst, int B, int C, int H, int W, cudaStream_t st) {
+    const long long n = (long long)B * C * H * (W / 4);
+    if (split)
+        polyphase_split_kernel<<<ofr::grid_for(n, 256, 8), 256, 0, st>>>(src, dst, B, C, H, W);
+    else
+        polyphase_merge_kernel<<<ofr::grid_for(n, 256, 8), 256, 0, st>>>(src, dst, B, C, H, W);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+// Can this geometry run as four stride-1 correlations on class images?  (instantiated for R = 10 only)
+bool polyphase_ok(const CorrGeom& g) {
+    return g.k == 1 && g.s1 == 1 && g.s2 == 2 && g.pad == g.md && g.md == 20 && (g.H % 2) == 0 && (g.W % 8) == 0;
+}
+CorrGeom class_geom(const CorrGeom& g) {
+    CorrGeom c = g;
+    c.B = g.B * 4, c.H = g.H / 2, c.W = g.W / 2;
+    c.pad = c.md = g.md / 2, c.s2 = 1;
+    c.r = c.md, c.D = g.D, c.Hout = c.H, c.Wout = c.W;
+    return c;
+}
+size_t poly_ws_bytes(const CorrGeom& g, bool backward) {
+    const size_t feat = ofr::align_up(sizeof(float) * (size_t)g.B * g.C * g.H * g.W, 256);
+    const size_t vol = ofr::align_up(sizeof(float) * (size_t)g.B * g.D * g.D * g.H * g.W, 256);
+    return backward ? 4 * feat + vol : 2 * feat + vol;
+}
+
 }  // namespace
 
 extern "C" int ofr_corr_out_shape(int H, int W, int pad, int k, int md, int s1, int s2, int* D, int* Hout,
@@ -319,11 +393,32 @@ extern "C" int ofr_corr_out_shape(int H, int W, int pad, int k, int md, int s1, 
     return OFR_OK;
 }
 
+extern "C" size_t ofr_corr_workspace(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2, int backward) {
+    CorrGeom g;
+    if (!make_geom(g, B, C, H, W, pad, k, md, s1, s2) || !polyphase_ok(g)) return 0;
+    return poly_ws_bytes(g, backward != 0);
+}
+
 extern "C" int ofr_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int pad, int k,
-                            int md, int s1, int s2, ofr_stream_t stream) {
+                            int md, int s1, int s2, void* ws, size_t ws_bytes, ofr_stream_t stream) {
     CorrGeom g;
     if (!f1 || !f2 || !out || !make_geom(g, B, C, H, W, pad, k, md, s1, s2)) return OFR_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (polyphase_ok(g) && ws && !(reinterpret_cast<uintptr_t>(ws) & 255u) && ws_bytes >= poly_ws_bytes(g, false) &&
+        ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(out)) {
+        // FlowNetC: Correlation(20,1,20,1,2) (FlowNetC.py:31) = 4 x stride-1 correlation (R = 10) on the class images
+        const size_t feat = ofr::align_up(sizeof(float) * (size_t)B * C * H * W, 256);
+        float* f1p = (float*)ws;
+        float* f2p = (float*)((char*)ws + feat);
+        float* outp = (float*)((char*)ws + 2 * feat);
+        const CorrGeom cg = class_geom(g);
+        int rc = polyphase(true, f1, f1p, B, C, H, W, st);
+        if (rc == OFR_OK) rc = polyphase(true, f2, f2p, B, C, H, W, st);
+        if (rc != OFR_OK) return rc;
+        rc = ofr::corr_fwd_tma(f1p, f2p, outp, cg, st);
+        if (rc == OFR_OK) return polyphase(false, outp, out, B, g.D * g.D, H, W, st);
+        if (rc != OFR_ENOTSUP) return rc;
+    }
     const bool vec_ok = k == 1 && s1 == 1 && (W % 4 == 0) && ((md - pad) % 4 == 0) && ((g.r * s2) % 4 == 0) &&
                         ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(out) && (g.Wout % 4 == 0);
     {  // PWC-Net: Correlation(4,1,4,1,1) (PWCNet.py:69) -> TMA-staged kernels
@@ -346,11 +441,37 @@ extern "C" int ofr_corr_fwd(const float* f1, const float* f2, float* out, int B,
 }
 
 extern "C" int ofr_corr_bwd(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, int B, int C,
-                            int H, int W, int pad, int k, int md, int s1, int s2, ofr_stream_t stream) {
+                            int H, int W, int pad, int k, int md, int s1, int s2, void* ws, size_t ws_bytes,
+                            ofr_stream_t stream) {
     CorrGeom g;
     if (!f1 || !f2 || !gO || !make_geom(g, B, C, H, W, pad, k, md, s1, s2)) return OFR_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (!gI1 && !gI2) return OFR_OK;
+    if (polyphase_ok(g) && ws && !(reinterpret_cast<uintptr_t>(ws) & 255u) && ws_bytes >= poly_ws_bytes(g, true) &&
+        ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(gO) && (!gI1 || ofr::aligned16(gI1)) &&
+        (!gI2 || ofr::aligned16(gI2))) {
+        const size_t feat = ofr::align_up(sizeof(float) * (size_t)B * C * H * W, 256);
+        const size_t vol = ofr::align_up(sizeof(float) * (size_t)B * g.D * g.D * H * W, 256);
+        char* w = (char*)ws;
+        float* f1p = (float*)w;
+        float* f2p = (float*)(w + feat);
+        float* gOp = (float*)(w + 2 * feat);
+        float* g1p = (float*)(w + 2 * feat + vol);
+        float* g2p = (float*)(w + 3 * feat + vol);
+        const CorrGeom cg = class_geom(g);
+        int rc = OFR_OK;
+        if (gI2) rc = polyphase(true, f1, f1p, B, C, H, W, st);
+        if (rc == OFR_OK && gI1) rc = polyphase(true, f2, f2p, B, C, H, W, st);
+        if (rc == OFR_OK) rc = polyphase(true, gO, gOp, B, g.D * g.D, H, W, st);
+        if (rc != OFR_OK) return rc;
+        rc = ofr::corr_bwd_tma(f1p, f2p, gOp, gI1 ? g1p : nullptr, gI2 ? g2p : nullptr, cg, st);
+        if (rc == OFR_OK) {
+            if (gI1) rc = polyphase(false, g1p, gI1, B, C, H, W, st);
+            if (rc == OFR_OK && gI2) rc = polyphase(false, g2p, gI2, B, C, H, W, st);
+            return rc;
+        }
+        if (rc != OFR_ENOTSUP) return rc;
+    }
     {
         const int rc = ofr::corr_bwd_tma(f1, f2, gO, gI1, gI2, g, st);
         if (rc != OFR_ENOTSUP) return rc;

@@ -1,19 +1,28 @@
-// TMA-staged correlation kernels for the PWC-Net configuration Correlation(4,1,4,1,1) (PWC/models/PWCNet.py:69):
-// k=1, stride1=1, stride2=1, pad == md == 4, D = 9, 81 output channels.
+// TMA-staged stride-1 correlation kernels (k = 1, stride1 = 1, stride2 = 1, pad == md == R, D = 2R+1).
+//   R = 4  : the PWC-Net configuration Correlation(4,1,4,1,1)               (PWC/models/PWCNet.py:69)
+//   R = 10 : the FlowNetC configuration Correlation(20,1,20,1,2) after the 2x2 polyphase split of correlation.cu:
+//            with stride2 = 2 a pixel only ever meets pixels of its own (y mod 2, x mod 2) class, so on each of the
+//            four half-resolution class images the operator IS a stride-1 correlation with R = 10
+//            (flownet2/networks/FlowNetC.py:31).
 //
-// Forward  (corr_fwd_tma_kernel): a CTA owns a TH x TW tile of one image.  One elected thread streams chunks of
-//   CK channels through an NST-deep ring of shared-memory stages with cp.async.bulk.tensor (TMA): the f1 tile and
-//   the f2 tile + 4-pixel displacement halo; out-of-image halo elements are zero-filled by the TMA unit, which is
-//   exactly the zero padding of the operator.  Each thread owns 8 pixels along x and the 9 x-displacements of ONE
-//   displacement row tj: the Toeplitz register tile acc[i][j] += a[i] * b[i+j] (72 FMAs per 6 128-bit LDS).  The 9
-//   tj-threads of a strip are adjacent lanes, so their `a` loads are one broadcast.  Channel sum = fixed-order loop.
-// Backward (corr_bwd_tma_kernel): the same Toeplitz tile, transposed.  A CTA owns an 8 x TW tile and 32 channels.
-//   The feature tile + halo of those 32 channels stays resident in shared memory; the 81 gradient planes stream
-//   through a 2-stage TMA ring, 9 planes (one displacement row) per stage.  A thread owns 8 pixels x 8 channels:
-//   acc[i][k] += g[ti][i] * b_k[i+ti].  Lanes that differ only in channel group broadcast the g loads.
+// Forward  (corr_fwd_tma_kernel): persistent CTAs (one per SM) walk the (image, tile) list.  One elected thread
+//   streams chunks of CK channels through an NST-deep ring of shared-memory stages with cp.async.bulk.tensor (TMA):
+//   the f1 tile and the f2 tile + R-pixel displacement halo; out-of-image halo elements are zero-filled by the TMA
+//   unit, which is exactly the zero padding of the operator.  The ring runs ahead across tile boundaries.
+//   Thread tile: M pixels along x  x  D x-displacements of ONE displacement row tj: acc[i][j] += a[i] * b[i+j].
+//   Shared-memory bandwidth is the scarce resource (a 128-bit LDS costs >= 4 wavefronts however many lanes share an
+//   address), so the lane mapping makes every quarter-warp bank-conflict free: lanes = 8 tj (fastest) x 4
+//   (strip,row) pairs and the f2 row pitch is 4*odd (mod 32) floats, so the 8 rows of a quarter-warp start in 8
+//   different bank groups.  Channel sum = fixed-order loop (no split-K, no atomics).  Epilogue: staged through shared
+//   memory and written with asynchronous TMA tensor stores (whole 128-byte lines, image-edge clipping for free).
+// Backward (corr_bwd_tma_kernel): the same Toeplitz tile, transposed.  A CTA owns a TH x TW tile and 32 channels.
+//   The feature tile + halo of those channels stays resident in shared memory; the D*D gradient planes stream
+//   through a 2-stage TMA ring, D planes (one displacement row) per stage.  A thread owns 8 pixels x CN channels:
+//   acc[i][k] += g[ti][i] * b_k[i+ti].
 //     gI1[c,p] = s * sum_t gO[t,p]      * f2[c,p+t]              (planes staged in place)
-//     gI2[c,q] = s * sum_t gO[-t,q+t]   * f1[c,q+t]              (plane -t staged with its box shifted by t:
-//                                                                  the same inner loop serves both gradients)
+//     gI2[c,q] = s * sum_t gO[-t,q+t]   * f1[c,q+t]              (plane -t staged as an aligned, widened box with
+//                                                                  its rows shifted by tj; the x shift is applied
+//                                                                  when the registers are filled)
 //   No atomics, fixed summation order -> bitwise reproducible.
 #include "corr_internal.cuh"
 #include "tma.cuh"
@@ -22,8 +31,6 @@ namespace {
 
 using ofr::CorrGeom;
 
-constexpr int kR = 4, kD = 9, kM = 8;
-
 __host__ __device__ constexpr int pitch_for(int cols) {  // multiple of 4, == 4*odd (mod 32)
     int p = (cols + 3) / 4 * 4;
     while ((p / 4) % 2 == 0 || p % 32 == 0) p += 4;
@@ -31,58 +38,67 @@ __host__ __device__ constexpr int pitch_for(int cols) {  // multiple of 4, == 4*
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// Persistent CTAs (one per SM) walk the (image, tile) list; the TMA ring runs ahead across tile boundaries, so the
-// loads of the next tile overlap the last chunks and the epilogue of the current one.
-//
-// Thread tile: M pixels along x  x  9 x-displacements of one displacement row tj  (acc[M][9], M = 16: 144 FMAs per
-// 10 128-bit LDS).  Shared-memory bandwidth is the scarce resource: a 128-bit LDS costs >= 4 wavefronts however many
-// lanes share an address, so the lane mapping is chosen to make every quarter-warp bank-conflict free:
-//   warps 0..  : lanes = 8 tj (fastest) x 4 (strip,row) pairs.  A quarter-warp = the 8 tj rows of one strip; the f2 row
-//                pitch is 4*odd (mod 32) floats, so the 8 rows start in 8 different bank groups.
-//   last warp(s): tj = 8, lanes = 8 rows (fastest) x strips, same argument with the f1 pitch (also 4*odd mod 32).
-template <int M, int TH, int NS, int CK, int NST>
+template <int R, int M, int TH, int NS, int CK, int NST>
 struct FwdT {
+    static constexpr int D = 2 * R + 1;
     static constexpr int TW = NS * M;
+    static constexpr int XO = (4 - R % 4) % 4;  // TMA box origins must be 16-byte aligned along x: start XO pixels further left
+    static constexpr int BL = (M + 2 * R + XO + 3) / 4 * 4;  // floats of an f2 row one thread reads
     static constexpr int P1 = pitch_for(TW);
-    static constexpr int P2 = pitch_for(TW + 2 * kR);
-    static constexpr int R2 = TH + 2 * kR;
+    static constexpr int P2 = pitch_for(TW - M + BL);
+    static constexpr int R2 = TH + 2 * R;
     static constexpr int F1 = CK * TH * P1;   // floats per stage
     static constexpr int F2 = CK * R2 * P2;
     static constexpr int STAGE = F1 + F2;
-    static constexpr int T1 = 8 * TH * NS;    // threads that own tj = 0..7
-    static constexpr int THREADS = kD * TH * NS;
+    // D = 9: 8 tj lanes per (row,strip) + one extra warp for tj = 8 (no idle lanes).  Otherwise ceil(D/8) groups of
+    // 8 tj lanes, the lanes with tj >= D idle.
+    static constexpr bool kNine = (D == 9);
+    static constexpr int TJG = (D + 7) / 8;
+    static constexpr int T1 = 8 * TH * NS;
+    static constexpr int THREADS = kNine ? D * TH * NS : 8 * TJG * TH * NS;
     static constexpr int OP = TH * TW;        // one output plane tile, floats
-    static constexpr int OS = kD * OP;        // epilogue staging buffer: the 9 planes {tj*9 + j} of one j
+    static constexpr int OS = D * OP;         // epilogue staging buffer: the D planes {tj*D + j} of one j
     static constexpr size_t SMEM = sizeof(float) * (STAGE * NST + 2 * OS) + 8 * NST + 1024;
     static_assert((F1 * 4) % 128 == 0 && (F2 * 4) % 128 == 0 && (OP * 4) % 128 == 0,
                   "TMA sources / destinations must stay 128-byte aligned");
     static_assert(M % 4 == 0 && THREADS <= 1024, "bad tile");
 };
 
-template <int M, int TH, int NS, int CK, int NST>
+template <int R, int M, int TH, int NS, int CK, int NST>
 __global__ void __maxnreg__(224)
     corr_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                         const __grid_constant__ CUtensorMap mapO, CorrGeom g, int tiles_x, int tiles_y) {
-    using T = FwdT<M, TH, NS, CK, NST>;
+    using T = FwdT<R, M, TH, NS, CK, NST>;
+    constexpr int D = T::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // round the base up to 1024 B with an offset (not an integer cast) so the pointer stays in the shared window: LDS, not LD
     float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
-    float* ostage = smem + T::STAGE * NST;  // [2][9][TH][TW]
+    float* ostage = smem + T::STAGE * NST;  // [2][D][TH][TW]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + 2 * T::OS);
 
     const int tid = threadIdx.x;
     int tj, s, row;
-    if (tid < T::T1) {
-        tj = tid & 7;
-        const int q = tid >> 3;
-        s = q % NS;
-        row = q / NS;
+    if (T::kNine) {
+        if (tid < T::T1) {
+            tj = tid & 7;
+            const int q = tid >> 3;
+            s = q % NS;
+            row = q / NS;
+        } else {  // the ninth displacement row: lanes = rows (fastest) x strips
+            tj = 8;
+            const int q = tid - T::T1;
+            row = q % TH;
+            s = q / TH;
+        }
     } else {
-        tj = 8;
-        const int q = tid - T::T1;
-        row = q % TH;
-        s = q / TH;
+        const int q = tid >> 3;
+        const int combo = q % (TH * NS);
+        tj = (q / (TH * NS)) * 8 + (tid & 7);
+        s = combo % NS;
+        row = combo / NS;
     }
+    const bool active = tj < D;
+    const int tjc = active ? tj : D - 1;  // idle lanes read valid shared memory and discard the result
 
     const int nchunks = (g.C + CK - 1) / CK;
     const int ntiles = tiles_x * tiles_y * g.B;
@@ -103,7 +119,7 @@ __global__ void __maxnreg__(224)
         float* dst = smem + st * T::STAGE;
         ofr::mbar_expect_tx(&bars[st], T::STAGE * 4);
         ofr::tma_load_4d(dst, &map1, &bars[st], x0, y0, c0, b);
-        ofr::tma_load_4d(dst + T::F1, &map2, &bars[st], x0 - kR, y0 - kR, c0, b);
+        ofr::tma_load_4d(dst + T::F1, &map2, &bars[st], x0 - R - T::XO, y0 - R, c0, b);
     };
     if (tid == 0) {
         ofr::tma_prefetch_desc(&map1);
@@ -116,35 +132,35 @@ __global__ void __maxnreg__(224)
     if (tid == 0)
         for (int i = 0; i < NST && i < total; ++i) issue(i);
 
-    float acc[M][kD];
+    float acc[M][D];
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-        for (int j = 0; j < kD; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < D; ++j) acc[i][j] = 0.f;
 
     int ck = 0, tile_k = 0;
     for (int q = 0; q < total; ++q) {
         const int st = q % NST;
         ofr::mbar_wait(&bars[st], (q / NST) & 1);
         const float* ap = smem + st * T::STAGE + row * T::P1 + s * M;
-        const float* bp = smem + st * T::STAGE + T::F1 + (row + tj) * T::P2 + s * M;
+        const float* bp = smem + st * T::STAGE + T::F1 + (row + tjc) * T::P2 + s * M;
 #pragma unroll 1
         for (int cc = 0; cc < CK; ++cc) {
-            float a[M], bv[M + 2 * kR];
+            float a[M], bv[T::BL];
 #pragma unroll
             for (int i = 0; i < M; i += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(ap + cc * TH * T::P1 + i);
                 a[i] = v.x, a[i + 1] = v.y, a[i + 2] = v.z, a[i + 3] = v.w;
             }
 #pragma unroll
-            for (int i = 0; i < M + 2 * kR; i += 4) {
+            for (int i = 0; i < T::BL; i += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(bp + cc * T::R2 * T::P2 + i);
                 bv[i] = v.x, bv[i + 1] = v.y, bv[i + 2] = v.z, bv[i + 3] = v.w;
             }
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
-                for (int j = 0; j < kD; ++j) acc[i][j] = fmaf(a[i], bv[i + j], acc[i][j]);
+                for (int j = 0; j < D; ++j) acc[i][j] = fmaf(a[i], bv[i + j + T::XO], acc[i][j]);
         }
         __syncthreads();  // every thread is done reading stage st
         if (tid == 0 && q + NST < total) {
@@ -153,56 +169,56 @@ __global__ void __maxnreg__(224)
         }
         if (++ck == nchunks) {
             // Tile finished.  Epilogue through shared memory and TMA stores: for each x-displacement j the CTA stages
-            // the 9 planes {tj*9 + j} (dense TH x TW boxes) and one thread issues 9 asynchronous tensor stores; the
+            // the D planes {tj*D + j} (dense TH x TW boxes) and one thread issues D asynchronous tensor stores; the
             // stores drain while the next tile is being computed, write whole 128-byte lines, and clip rows / columns
             // outside the image by themselves.  Two staging buffers alternate.
             int x0, y0, b;
             tile_origin(tile_k, x0, y0, b);
             const int rot = tj & 3;  // 16-byte chunk rotation: halves the bank conflicts of the 8 tj lanes of a quarter-warp
 #pragma unroll
-            for (int j = 0; j < kD; ++j) {
-                float* buf = ostage + ((j + tile_k) & 1) * T::OS;  // 9 is odd: tile_k keeps consecutive groups alternating
+            for (int j = 0; j < D; ++j) {
+                float* buf = ostage + ((j + tile_k * D) & 1) * T::OS;  // D is odd: keep consecutive groups alternating
                 if (tid == 0) ofr::tma_store_wait_read<1>();  // the group that last read this buffer is done with it
                 __syncthreads();
-                float* dst = buf + tj * T::OP + row * T::TW + s * M;
-#pragma unroll
-                for (int i0 = 0; i0 < M; i0 += 16) {
-                    float4 c[4];
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const int i = i0 + 4 * qd;
-                        c[qd] = (i < M) ? make_float4(acc[i % M][j] * g.scale, acc[(i + 1) % M][j] * g.scale,
-                                                      acc[(i + 2) % M][j] * g.scale, acc[(i + 3) % M][j] * g.scale)
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                if (active) {
+                    float* dst = buf + tj * T::OP + row * T::TW + s * M;
                     if (M >= 16) {
-                        // rotate the four chunks left by `rot` with selects (registers cannot be indexed dynamically)
-                        float4 d[4];
 #pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            const float4 p0 = c[qd], p1 = c[(qd + 1) & 3], p2 = c[(qd + 2) & 3], p3 = c[(qd + 3) & 3];
-                            d[qd] = rot == 0 ? p0 : rot == 1 ? p1 : rot == 2 ? p2 : p3;
+                        for (int i0 = 0; i0 < M; i0 += 16) {
+                            float4 c[4];
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                const int i = i0 + 4 * qd;
+                                c[qd] = make_float4(acc[i % M][j] * g.scale, acc[(i + 1) % M][j] * g.scale,
+                                                    acc[(i + 2) % M][j] * g.scale, acc[(i + 3) % M][j] * g.scale);
+                            }
+                            // rotate the four chunks left by `rot` with selects (registers cannot be indexed dynamically)
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                const float4 p0 = c[qd], p1 = c[(qd + 1) & 3], p2 = c[(qd + 2) & 3], p3 = c[(qd + 3) & 3];
+                                const float4 d = rot == 0 ? p0 : rot == 1 ? p1 : rot == 2 ? p2 : p3;
+                                *reinterpret_cast<float4*>(dst + i0 + 4 * ((qd + rot) & 3)) = d;
+                            }
                         }
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd)
-                            *reinterpret_cast<float4*>(dst + i0 + 4 * ((qd + rot) & 3)) = d[qd];
                     } else {
 #pragma unroll
-                        for (int qd = 0; qd < M / 4; ++qd) *reinterpret_cast<float4*>(dst + i0 + 4 * qd) = c[qd];
+                        for (int i = 0; i < M; i += 4)
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i][j] * g.scale, acc[i + 1][j] * g.scale,
+                                                                              acc[i + 2][j] * g.scale, acc[i + 3][j] * g.scale);
                     }
                 }
                 ofr::fence_proxy_async();  // make the generic-proxy writes visible to the TMA engine
                 __syncthreads();
                 if (tid == 0) {
-#pragma unroll
-                    for (int t = 0; t < kD; ++t) ofr::tma_store_4d(&mapO, buf + t * T::OP, x0, y0, t * kD + j, b);
+#pragma unroll 1
+                    for (int t = 0; t < D; ++t) ofr::tma_store_4d(&mapO, buf + t * T::OP, x0, y0, t * D + j, b);
                     ofr::tma_store_commit();
                 }
             }
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
-                for (int j = 0; j < kD; ++j) acc[i][j] = 0.f;
+                for (int j = 0; j < D; ++j) acc[i][j] = 0.f;
             ck = 0;
             ++tile_k;
         }
@@ -210,14 +226,14 @@ __global__ void __maxnreg__(224)
     if (tid == 0) ofr::tma_store_wait_all<0>();  // shared memory must outlive the stores that read it
 }
 
-template <int M, int TH, int NS, int CK, int NST>
+template <int R, int M, int TH, int NS, int CK, int NST>
 int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
-    using T = FwdT<M, TH, NS, CK, NST>;
+    using T = FwdT<R, M, TH, NS, CK, NST>;
     CUtensorMap m1, m2, mo;
     if (!ofr::make_tmap_nchw(&m1, f1, g.B, g.C, g.H, g.W, T::P1, TH, CK)) return OFR_ENOTSUP;
     if (!ofr::make_tmap_nchw(&m2, f2, g.B, g.C, g.H, g.W, T::P2, T::R2, CK)) return OFR_ENOTSUP;
-    if (!ofr::make_tmap_nchw(&mo, out, g.B, kD * kD, g.Hout, g.Wout, T::TW, TH, 1)) return OFR_ENOTSUP;
-    auto kern = corr_fwd_tma_kernel<M, TH, NS, CK, NST>;
+    if (!ofr::make_tmap_nchw(&mo, out, g.B, T::D * T::D, g.Hout, g.Wout, T::TW, TH, 1)) return OFR_ENOTSUP;
+    auto kern = corr_fwd_tma_kernel<R, M, TH, NS, CK, NST>;
     OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
     const int tiles_x = (g.Wout + T::TW - 1) / T::TW, tiles_y = (g.Hout + TH - 1) / TH;
     const long long ntiles = (long long)tiles_x * tiles_y * g.B;
@@ -230,34 +246,95 @@ int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, 
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int kBTH = 8;    // tile rows
+constexpr int kBM = 8;     // pixels per thread along x
 constexpr int kCB = 32;    // channels per CTA
-constexpr int kCG = 4;     // channel groups (lanes); each thread owns kCB / kCG = 8 channels, c = k*4 + cg
-constexpr int kCN = kCB / kCG;
 
-template <int NS, bool SHIFTED>
+// CG channel groups (lanes) x CN channels per thread = kCB; the thread's channels are c = k*CG + cg.
+// TIC = x-displacements handled per register sweep (D must be a multiple of TIC).
+template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED>
 struct BwdT {
-    static constexpr int TW = NS * kM;
-    static constexpr int P2 = pitch_for(TW + 2 * kR);
-    static constexpr int R2 = kBTH + 2 * kR + 1;  // +1 row: makes the channel pitch == 4*odd (mod 32) -> cg lanes hit distinct banks
+    static constexpr int D = 2 * R + 1;
+    static constexpr int CN = kCB / CG;
+    static constexpr int TW = NS * kBM;
+    static constexpr int XO = (4 - R % 4) % 4;  // TMA box origins must be 16-byte aligned along x: start XO pixels further left
+    static constexpr int P2 = pitch_for(TW + 2 * R + XO + 3);
+    static constexpr int R2 = ((TH + 2 * R) * P2 / 4) % 2 == 1 ? TH + 2 * R : TH + 2 * R + 1;  // channel pitch 4*odd (mod 32)
     static constexpr int FT = kCB * R2 * P2;      // resident feature tile, floats
     // TMA needs a 16-byte aligned box origin along x, so the shifted planes of the second gradient are staged as
-    // aligned boxes widened by the halo and the +-4 pixel shift is applied when the registers are filled.
+    // aligned boxes widened by the halo and the +-R pixel shift is applied when the registers are filled.
     // row pitch of a staged gradient plane: 4*odd (mod 32) floats, so the 8 rows read by a quarter-warp hit 8 bank groups
-    static constexpr int GW = pitch_for(SHIFTED ? TW + 2 * kR : TW);
-    static constexpr int GP = kBTH * GW;                    // one plane tile, floats
-    static constexpr int GS = kD * GP;                      // one gradient stage (9 planes), floats
-    static constexpr int THREADS = kBTH * NS * kCG;
+    static constexpr int GW = pitch_for(SHIFTED ? TW + 2 * R + XO + 3 : TW);
+    static constexpr int GP = TH * GW;            // one plane tile, floats
+    static constexpr int GS = D * GP;             // one gradient stage (D planes), floats
+    static constexpr int THREADS = TH * NS * CG;
     static constexpr size_t SMEM = sizeof(float) * (FT + 2 * GS) + 8 * 3 + 1024;
     static_assert((FT * 4) % 128 == 0 && (GP * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(((R2 * P2) / 4) % 2 == 1, "channel pitch must be 4*odd (mod 32)");
+    static_assert(D % TIC == 0 && TH % 8 == 0 && kCB % CG == 0, "bad tile");
+    static_assert(SMEM <= 227 * 1024, "tile does not fit in shared memory");
 };
 
-template <int NS, bool SHIFTED>
-__global__ void __launch_bounds__(BwdT<NS, SHIFTED>::THREADS, 1)
+// one sweep over the x-displacements [T0, T0+TIC) of the staged displacement row
+template <class T, int R, int CG, int TIC, bool SHIFTED, int T0>
+__device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const float* __restrict__ fp,
+                                          float (&acc)[kBM][T::CN]) {
+    float gv[TIC][kBM];
+    if (SHIFTED) {
+        // the value for target x sits at column x - (x0 - R) + ti = s*8 + i + tii of the widened box: load the aligned
+        // window that covers [T0, T0 + TIC + 7) and pick the shifted 8 values per displacement
+#pragma unroll
+        for (int t = 0; t < TIC; ++t) {
+            constexpr int LEN = kBM + 4;  // aligned window that covers 8 values starting anywhere inside a float4
+            const int a0 = (T0 + t + T::XO) & ~3;
+            float w[LEN];
+#pragma unroll
+            for (int i = 0; i < LEN; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + a0 + i);
+                w[i] = v.x, w[i + 1] = v.y, w[i + 2] = v.z, w[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kBM; ++i) gv[t][i] = w[i + ((T0 + t + T::XO) & 3)];
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < TIC; ++t) {
+            const float4 v0 = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP);
+            const float4 v1 = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + 4);
+            gv[t][0] = v0.x, gv[t][1] = v0.y, gv[t][2] = v0.z, gv[t][3] = v0.w;
+            gv[t][4] = v1.x, gv[t][5] = v1.y, gv[t][6] = v1.z, gv[t][7] = v1.w;
+        }
+    }
+    constexpr int B0 = (T0 + T::XO) & ~3;                                // aligned start of the feature window
+    constexpr int BL = ((T0 + T::XO + TIC + kBM - 1) - B0 + 3) / 4 * 4;  // floats to load
+#pragma unroll
+    for (int k = 0; k < T::CN; ++k) {
+        float bv[BL];
+#pragma unroll
+        for (int i = 0; i < BL; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(fp + k * CG * T::R2 * T::P2 + B0 + i);
+            bv[i] = v.x, bv[i + 1] = v.y, bv[i + 2] = v.z, bv[i + 3] = v.w;
+        }
+#pragma unroll
+        for (int t = 0; t < TIC; ++t)
+#pragma unroll
+            for (int i = 0; i < kBM; ++i) acc[i][k] = fmaf(gv[t][i], bv[i + T0 + t + T::XO - B0], acc[i][k]);
+    }
+}
+
+template <class T, int R, int CG, int TIC, bool SHIFTED, int T0>
+struct SweepAll {
+    static __device__ __forceinline__ void run(const float* gp, const float* fp, float (&acc)[kBM][T::CN]) {
+        bwd_sweep<T, R, CG, TIC, SHIFTED, T0>(gp, fp, acc);
+        if constexpr (T0 + TIC < T::D) SweepAll<T, R, CG, TIC, SHIFTED, T0 + TIC>::run(gp, fp, acc);
+    }
+};
+
+template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED>
+__global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED>::THREADS, 1)
     corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapG,
                         float* __restrict__ gI, CorrGeom g, int tiles_x, int tiles_y, int cblocks) {
-    using T = BwdT<NS, SHIFTED>;
+    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED>;
+    constexpr int D = T::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* Fs = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
     float* Gs = Fs + T::FT;
@@ -270,25 +347,25 @@ __global__ void __launch_bounds__(BwdT<NS, SHIFTED>::THREADS, 1)
     bid /= tiles_y;
     const int cbi = bid % cblocks;
     const int b = bid / cblocks;
-    const int x0 = txi * T::TW, y0 = tyi * kBTH, c0 = cbi * kCB;
+    const int x0 = txi * T::TW, y0 = tyi * TH, c0 = cbi * kCB;
 
-    // lanes: 8 rows (fastest) x 4 channel groups of ONE strip -> a quarter-warp reads 8 different rows of the feature /
+    // lanes: rows (fastest) x channel groups of ONE strip -> a quarter-warp reads 8 different rows of the feature /
     // gradient tiles, whose pitches are 4*odd (mod 32): conflict-free 128-bit LDS
     const int tid = threadIdx.x;
-    const int row = tid % kBTH;
-    const int cg = (tid / kBTH) % kCG;
-    const int s = tid / (kBTH * kCG);
+    const int row = tid % TH;
+    const int cg = (tid / TH) % CG;
+    const int s = tid / (TH * CG);
 
     auto issue_g = [&](int tji, int st) {
         float* dst = Gs + st * T::GS;
         ofr::mbar_expect_tx(&bars[st], T::GS * 4);
-#pragma unroll
-        for (int tii = 0; tii < kD; ++tii) {
+#pragma unroll 1
+        for (int tii = 0; tii < D; ++tii) {
             if (SHIFTED)  // plane of displacement -t, rows shifted by tj here, columns shifted by ti at register fill
-                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0 - kR, y0 + tji - kR,
-                                 (2 * kR - tji) * kD + (2 * kR - tii), b);
+                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0 - R - T::XO, y0 + tji - R,
+                                 (2 * R - tji) * D + (2 * R - tii), b);
             else
-                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0, y0, tji * kD + tii, b);
+                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0, y0, tji * D + tii, b);
         }
     };
     if (tid == 0) {
@@ -302,101 +379,79 @@ __global__ void __launch_bounds__(BwdT<NS, SHIFTED>::THREADS, 1)
     __syncthreads();
     if (tid == 0) {
         ofr::mbar_expect_tx(&bars[2], T::FT * 4);
-        ofr::tma_load_4d(Fs, &mapF, &bars[2], x0 - kR, y0 - kR, c0, b);
+        ofr::tma_load_4d(Fs, &mapF, &bars[2], x0 - R - T::XO, y0 - R, c0, b);
         issue_g(0, 0);
         issue_g(1, 1);
     }
 
-    float acc[kM][kCN];
+    float acc[kBM][T::CN];
 #pragma unroll
-    for (int i = 0; i < kM; ++i)
+    for (int i = 0; i < kBM; ++i)
 #pragma unroll
-        for (int k = 0; k < kCN; ++k) acc[i][k] = 0.f;
+        for (int k = 0; k < T::CN; ++k) acc[i][k] = 0.f;
 
     ofr::mbar_wait(&bars[2], 0);
-    for (int tji = 0; tji < kD; ++tji) {
+    for (int tji = 0; tji < D; ++tji) {
         const int st = tji & 1;
         ofr::mbar_wait(&bars[st], (tji >> 1) & 1);
-        const float* gp = Gs + st * T::GS + row * T::GW + s * kM;
-        float gv[kD][kM];
-#pragma unroll
-        for (int tii = 0; tii < kD; ++tii) {
-            if (SHIFTED) {  // value for target x sits at column x - (x0 - R) + ti = s*8 + i + tii of the widened box
-                float w[kM + 2 * kR];
-#pragma unroll
-                for (int i = 0; i < kM + 2 * kR; i += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(gp + tii * T::GP + i);
-                    w[i] = v.x, w[i + 1] = v.y, w[i + 2] = v.z, w[i + 3] = v.w;
-                }
-#pragma unroll
-                for (int i = 0; i < kM; ++i) gv[tii][i] = w[i + tii];
-            } else {
-                const float4 v0 = *reinterpret_cast<const float4*>(gp + tii * T::GP);
-                const float4 v1 = *reinterpret_cast<const float4*>(gp + tii * T::GP + 4);
-                gv[tii][0] = v0.x, gv[tii][1] = v0.y, gv[tii][2] = v0.z, gv[tii][3] = v0.w;
-                gv[tii][4] = v1.x, gv[tii][5] = v1.y, gv[tii][6] = v1.z, gv[tii][7] = v1.w;
-            }
-        }
-        const float* fp = Fs + (long long)cg * T::R2 * T::P2 + (row + tji) * T::P2 + s * kM;
-#pragma unroll
-        for (int k = 0; k < kCN; ++k) {
-            float bv[kM + 2 * kR];
-#pragma unroll
-            for (int i = 0; i < kM + 2 * kR; i += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(fp + k * kCG * T::R2 * T::P2 + i);
-                bv[i] = v.x, bv[i + 1] = v.y, bv[i + 2] = v.z, bv[i + 3] = v.w;
-            }
-#pragma unroll
-            for (int tii = 0; tii < kD; ++tii)
-#pragma unroll
-                for (int i = 0; i < kM; ++i) acc[i][k] = fmaf(gv[tii][i], bv[i + tii], acc[i][k]);
-        }
+        const float* gp = Gs + st * T::GS + row * T::GW + s * kBM;
+        const float* fp = Fs + (long long)cg * T::R2 * T::P2 + (row + tji) * T::P2 + s * kBM;
+        SweepAll<T, R, CG, TIC, SHIFTED, 0>::run(gp, fp, acc);
         __syncthreads();
-        if (tid == 0 && tji + 2 < kD) {
+        if (tid == 0 && tji + 2 < D) {
             ofr::fence_proxy_async();
             issue_g(tji + 2, st);
         }
     }
 
-    const int y = y0 + row, xb = x0 + s * kM;
+    const int y = y0 + row, xb = x0 + s * kBM;
     if (y < g.H) {
         const long long hw = (long long)g.H * g.W;
 #pragma unroll
-        for (int k = 0; k < kCN; ++k) {
-            const int c = c0 + k * kCG + cg;
+        for (int k = 0; k < T::CN; ++k) {
+            const int c = c0 + k * CG + cg;
             if (c >= g.C) continue;
             float* o = gI + ((long long)b * g.C + c) * hw + (long long)y * g.W;
-            if (xb + kM <= g.W) {
+            if (xb + kBM <= g.W) {
                 *reinterpret_cast<float4*>(o + xb) = make_float4(acc[0][k] * g.scale, acc[1][k] * g.scale, acc[2][k] * g.scale, acc[3][k] * g.scale);
                 *reinterpret_cast<float4*>(o + xb + 4) = make_float4(acc[4][k] * g.scale, acc[5][k] * g.scale, acc[6][k] * g.scale, acc[7][k] * g.scale);
             } else {
 #pragma unroll
-                for (int i = 0; i < kM; ++i)
+                for (int i = 0; i < kBM; ++i)
                     if (xb + i < g.W) o[xb + i] = acc[i][k] * g.scale;
             }
         }
     }
 }
 
-template <int NS, bool SHIFTED>
+template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED>
 int launch_bwd(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
-    using T = BwdT<NS, SHIFTED>;
+    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED>;
     CUtensorMap mF, mG;
     if (!ofr::make_tmap_nchw(&mF, feat, g.B, g.C, g.H, g.W, T::P2, T::R2, kCB)) return OFR_ENOTSUP;
-    if (!ofr::make_tmap_nchw(&mG, gO, g.B, kD * kD, g.Hout, g.Wout, T::GW, kBTH, 1)) return OFR_ENOTSUP;
-    auto kern = corr_bwd_tma_kernel<NS, SHIFTED>;
+    if (!ofr::make_tmap_nchw(&mG, gO, g.B, T::D * T::D, g.Hout, g.Wout, T::GW, TH, 1)) return OFR_ENOTSUP;
+    auto kern = corr_bwd_tma_kernel<R, TH, NS, CG, TIC, SHIFTED>;
     OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-    const int tiles_x = (g.W + T::TW - 1) / T::TW, tiles_y = (g.H + kBTH - 1) / kBTH;
+    const int tiles_x = (g.W + T::TW - 1) / T::TW, tiles_y = (g.H + TH - 1) / TH;
     const int cblocks = (g.C + kCB - 1) / kCB;
-    kern<<<(unsigned)(tiles_x * tiles_y * cblocks * g.B), T::THREADS, T::SMEM, st>>>(mF, mG, gI, g, tiles_x, tiles_y, cblocks);
+    const long long nblk = (long long)tiles_x * tiles_y * cblocks * g.B;
+    if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
+    kern<<<(unsigned)nblk, T::THREADS, T::SMEM, st>>>(mF, mG, gI, g, tiles_x, tiles_y, cblocks);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
 
-bool applicable(const CorrGeom& g, const void* a, const void* b, const void* c) {
-    return g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == kR && g.pad == kR && (g.W % 4) == 0 && ofr::aligned16(a) &&
-           ofr::aligned16(b) && ofr::aligned16(c) && ofr::encode_tiled_fn() != nullptr &&
-           (long long)g.B * 4096 * ((g.W + 7) / 8) * ((g.H + 7) / 8) < (1ll << 31);
+template <bool SHIFTED>
+int dispatch_bwd4(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
+    if (g.W > 32) return launch_bwd<4, 8, 8, 4, 9, SHIFTED>(feat, gO, gI, g, st);
+    if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, SHIFTED>(feat, gO, gI, g, st);
+    if (g.W > 8) return launch_bwd<4, 8, 2, 4, 9, SHIFTED>(feat, gO, gI, g, st);
+    return launch_bwd<4, 8, 1, 4, 9, SHIFTED>(feat, gO, gI, g, st);
+}
+
+bool applicable(const CorrGeom& g, int R, const void* a, const void* b, const void* c) {
+    return g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == R && g.pad == R && (g.W % 4) == 0 && ofr::aligned16(a) &&
+           ofr::aligned16(b) && ofr::aligned16(c) && ofr::encode_tiled_fn() != nullptr;
 }
 
 }  // namespace
@@ -404,33 +459,36 @@ bool applicable(const CorrGeom& g, const void* a, const void* b, const void* c) 
 namespace ofr {
 
 int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
-    if (!applicable(g, f1, f2, out)) return OFR_ENOTSUP;
-    // 7 rows: 7 warps own tj = 0..7 and one warp owns tj = 8 -> 8 warps; a 9-warp CTA would be allocated registers
-    // for 12 warps and could not keep the 144 accumulators of the 16-pixel strip
-    if (g.W > 32) return launch_fwd<16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
-    if (g.W > 16) return launch_fwd<16, 8, 2, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads
-    if (g.W > 8) return launch_fwd<16, 8, 1, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile,  72 threads
-    return launch_fwd<8, 8, 1, 8, 4>(f1, f2, out, g, st);                  // 8 x 8 tile,   72 threads
+    if (applicable(g, 4, f1, f2, out)) {
+        // 7 rows: 7 warps own tj = 0..7 and one warp owns tj = 8 -> 8 warps; a 9-warp CTA would be allocated registers
+        // for 12 warps and could not keep the 144 accumulators of the 16-pixel strip
+        if (g.W > 32) return launch_fwd<4, 16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
+        if (g.W > 16) return launch_fwd<4, 16, 8, 2, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads
+        if (g.W > 8) return launch_fwd<4, 16, 8, 1, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile,  72 threads
+        return launch_fwd<4, 8, 8, 1, 8, 4>(f1, f2, out, g, st);                  // 8 x 8 tile,   72 threads
+    }
+    if (applicable(g, 10, f1, f2, out))
+        return launch_fwd<10, 8, 4, 2, 8, 3>(f1, f2, out, g, st);                 // 4 x 16 tile, 192 threads (3 x 8 tj lanes)
+    return OFR_ENOTSUP;
 }
 
 int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
                  cudaStream_t st) {
-    if (!applicable(g, f1, f2, gO) || (gI1 && !ofr::aligned16(gI1)) || (gI2 && !ofr::aligned16(gI2))) return OFR_ENOTSUP;
+    if ((gI1 && !ofr::aligned16(gI1)) || (gI2 && !ofr::aligned16(gI2))) return OFR_ENOTSUP;
     int rc = OFR_OK;
-    if (gI1) {
-        if (g.W > 32) rc = launch_bwd<8, false>(f2, gO, gI1, g, st);
-        else if (g.W > 16) rc = launch_bwd<4, false>(f2, gO, gI1, g, st);
-        else if (g.W > 8) rc = launch_bwd<2, false>(f2, gO, gI1, g, st);
-        else rc = launch_bwd<1, false>(f2, gO, gI1, g, st);
-        if (rc != OFR_OK) return rc;
+    if (applicable(g, 4, f1, f2, gO)) {
+        if (gI1) rc = dispatch_bwd4<false>(f2, gO, gI1, g, st);
+        if (rc == OFR_OK && gI2) rc = dispatch_bwd4<true>(f1, gO, gI2, g, st);
+        return rc;
     }
-    if (gI2) {
-        if (g.W > 32) rc = launch_bwd<8, true>(f1, gO, gI2, g, st);
-        else if (g.W > 16) rc = launch_bwd<4, true>(f1, gO, gI2, g, st);
-        else if (g.W > 8) rc = launch_bwd<2, true>(f1, gO, gI2, g, st);
-        else rc = launch_bwd<1, true>(f1, gO, gI2, g, st);
+    if (applicable(g, 10, f1, f2, gO)) {
+        // R = 10 (class images of FlowNetC, 16 x 16 or 32 x 32): 8 x 16 tiles, 8 channel groups x 4 channels, 7
+        // x-displacements per register sweep
+        if (gI1) rc = launch_bwd<10, 8, 2, 8, 7, false>(f2, gO, gI1, g, st);
+        if (rc == OFR_OK && gI2) rc = launch_bwd<10, 8, 2, 8, 7, true>(f1, gO, gI2, g, st);
+        return rc;
     }
-    return rc;
+    return OFR_ENOTSUP;
 }
 
 }  // namespace ofr

@@ -70,8 +70,10 @@ class _CorrelationFn(torch.autograd.Function):
         out = torch.empty(B, D * D, Ho, Wo, dtype=torch.float32, device=input1.device)
         nbytes = 4 * (2 * B * C * H * W + B * D * D * Ho * Wo)
         with torch.cuda.device(input1.device), region(f"corr_fwd C{C} {H}x{W} D{D}", nbytes, 2 * B * D * D * C * Ho * Wo):
+            ws_bytes = int(_lib.lib().ofr_corr_workspace(B, C, H, W, pad, k, md, s1, s2, 0))
+            ws = _workspace(ws_bytes, input1.device) if ws_bytes else None
             _lib.check(_lib.lib().ofr_corr_fwd(_ptr(input1), _ptr(input2), _ptr(out), B, C, H, W, pad, k, md, s1, s2,
-                                               _stream()), "ofr_corr_fwd")
+                                               _ptr(ws), ws_bytes, _stream()), "ofr_corr_fwd")
         ctx.save_for_backward(input1, input2)
         ctx.geom = (pad, k, md, s1, s2)
         return out
@@ -90,8 +92,11 @@ class _CorrelationFn(torch.autograd.Function):
             nbytes = 4 * (2 * B * C * H * W + grad_out.numel() + ng * B * C * H * W)
             with torch.cuda.device(input1.device), region(f"corr_bwd C{C} {H}x{W} D2={Dd} g{ng}", nbytes,
                                                           2 * ng * grad_out.numel() * C):
+                ws_bytes = int(_lib.lib().ofr_corr_workspace(B, C, H, W, pad, k, md, s1, s2, 1))
+                ws = _workspace(ws_bytes, input1.device) if ws_bytes else None
                 _lib.check(_lib.lib().ofr_corr_bwd(_ptr(input1), _ptr(input2), _ptr(grad_out), _ptr(g1), _ptr(g2),
-                                                   B, C, H, W, pad, k, md, s1, s2, _stream()), "ofr_corr_bwd")
+                                                   B, C, H, W, pad, k, md, s1, s2, _ptr(ws), ws_bytes, _stream()),
+                           "ofr_corr_bwd")
         return g1, g2, None, None, None, None, None
 
 

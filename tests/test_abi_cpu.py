@@ -29,7 +29,7 @@ def test_header_symbols_all_exported(built):
 
 def test_abi_version_and_error_strings(built):
     lib = built._lib.lib()
-    assert lib.ofr_abi_version() == 1
+    assert lib.ofr_abi_version() == 2
     assert lib.ofr_error_string(0) == b"ok"
     for code in (1, 2, 3):
         assert len(lib.ofr_error_string(code)) > 5
@@ -47,8 +47,10 @@ def test_host_side_argument_checks_need_no_gpu(built):
         built.correlation_out_shape(4, 4, 0, 1, 4, 1, 1)  # empty output
     # null pointers / bad dims are rejected before any launch
     assert lib.ofr_chnorm_fwd(None, None, 1, 1, 1, 1, None) == 1
-    assert lib.ofr_corr_fwd(None, None, None, 1, 1, 8, 8, 4, 1, 4, 1, 1, None) == 1
-    assert lib.ofr_corr_fwd(1, 1, 1, 1, 1, 8, 8, 4, 2, 4, 1, 1, None) == 1  # even kernel size
+    assert lib.ofr_corr_fwd(None, None, None, 1, 1, 8, 8, 4, 1, 4, 1, 1, None, 0, None) == 1
+    assert lib.ofr_corr_fwd(1, 1, 1, 1, 1, 8, 8, 4, 2, 4, 1, 1, None, 0, None) == 1  # even kernel size
+    assert lib.ofr_corr_workspace(24, 32, 128, 128, 4, 1, 4, 1, 1, 0) == 0        # PWC path needs no scratch
+    assert lib.ofr_corr_workspace(1, 4, 32, 32, 20, 1, 20, 1, 2, 0) >= 4 * (2 * 4 + 441) * 32 * 32
     assert lib.ofr_resample_fwd(None, None, None, 1, 1, 4, 4, 4, 4, 0, None) == 1
     assert lib.ofr_loss_workspace(0) == 0 and lib.ofr_loss_workspace(9) == 0
     assert lib.ofr_loss_workspace(7) > 0

@@ -47,10 +47,14 @@ def cases(B, S):
         go = torch.randn_like(o)
         g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
         flops = 2 * B * D * D * C * h * h
+        wf = int(L.ofr_corr_workspace(B, C, h, h, pad, 1, md, 1, s2, 0))
+        wb = int(L.ofr_corr_workspace(B, C, h, h, pad, 1, md, 1, s2, 1))
+        ws = torch.empty(max(wf, wb, 256), dtype=torch.uint8, device=DEV)
         out.append((f"corr_fwd {tag} C{C} {h}x{h}", 4 * (2 * f1.numel() + o.numel()), flops,
-                    lambda: L.ofr_corr_fwd(P(f1), P(f2), P(o), B, C, h, h, pad, 1, md, 1, s2, stream())))
+                    lambda: L.ofr_corr_fwd(P(f1), P(f2), P(o), B, C, h, h, pad, 1, md, 1, s2, P(ws), wf, stream())))
         out.append((f"corr_bwd {tag} C{C} {h}x{h}", 4 * (4 * f1.numel() + o.numel()), 2 * flops,
-                    lambda: L.ofr_corr_bwd(P(f1), P(f2), P(go), P(g1), P(g2), B, C, h, h, pad, 1, md, 1, s2, stream())))
+                    lambda: L.ofr_corr_bwd(P(f1), P(f2), P(go), P(g1), P(g2), B, C, h, h, pad, 1, md, 1, s2, P(ws), wb,
+                                           stream())))
 
     def warp(tag, C, h, mode, want1, sigma):
         x = torch.randn(B, C, h, h, device=DEV)
