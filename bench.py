@@ -88,11 +88,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ model builders
-def build_gpu_step(device):
+def build_gpu_step(device, channels_last=False):
     import ofr_b200 as ofr
     from ofr_b200.harness import PWCNetHost, RegistrationStep
     torch.manual_seed(6)
     host = PWCNetHost(md=4).to(device)
+    if channels_last:  # host-model memory format only; the ofr_b200 layers take / return NCHW (they call .contiguous())
+        host = host.to(memory_format=torch.channels_last)
     host.deconv0.requires_grad_(False)  # unused in the forward (PWCNet.py:126,274): keep it out of DDP's reducer
     return RegistrationStep(host, ofr.stn_warp, ofr.OFEloss), ofr
 
@@ -168,7 +170,8 @@ def run_ours(args):
     from ofr_b200.harness import synthetic_pairs, make_optimizer, train_step
     from ofr_b200.profiling import KernelTimer
 
-    step, ofr = build_gpu_step(device)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    step, ofr = build_gpu_step(device, channels_last=args.channels_last)
     if world > 1:
         step.predictor = torch.nn.parallel.DistributedDataParallel(step.predictor, device_ids=[local],
                                                                    gradient_as_bucket_view=True)
@@ -249,6 +252,8 @@ def run_ours(args):
             "config": {"workload": f"pwcnet_train_b{B}_{S}x{S}", "per_gpu_batch": B, "global_batch": world * B,
                        "host_model": "PWCNetHost (PWC-DC-Net 1ch, 9374184 params; cuDNN convs, TF32 conv default)",
                        "optimizer": "Adam(lr=1e-4, eps=1e-4)", "parallelism": f"dp{world}",
+                       "host_memory_format": "channels_last" if args.channels_last else "contiguous (NCHW)",
+                       "cudnn_benchmark": bool(args.cudnn_benchmark),
                        "l2": "working set (activations > 1 GB per step) exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "kernels": rows[:24], "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_host.numel() * 4 * world,
@@ -270,6 +275,8 @@ def main():
     ap.add_argument("--batch", type=int, default=24, help="slice pairs per GPU (train.py default batch_size 24)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: pairs per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels-last", type=int, default=0, help="host model (cuDNN convolutions) in channels_last")
+    ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the host model")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

@@ -258,18 +258,18 @@ struct BwdT {
     static constexpr int TW = NS * kBM;
     static constexpr int XO = (4 - R % 4) % 4;  // TMA box origins must be 16-byte aligned along x: start XO pixels further left
     static constexpr int P2 = pitch_for(TW + 2 * R + XO + 3);
-    static constexpr int R2 = ((TH + 2 * R) * P2 / 4) % 2 == 1 ? TH + 2 * R : TH + 2 * R + 1;  // channel pitch 4*odd (mod 32)
+    static constexpr int R2 = TH + 2 * R;
     static constexpr int FT = kCB * R2 * P2;      // resident feature tile, floats
-    // TMA needs a 16-byte aligned box origin along x, so the shifted planes of the second gradient are staged as
-    // aligned boxes widened by the halo and the +-R pixel shift is applied when the registers are filled.
+    // TMA needs a 16-byte aligned box origin along x, so each shifted plane of the second gradient is staged as a box
+    // whose origin is rounded down to a multiple of 4 pixels (4 extra columns) and the residual 0..3 pixel shift is
+    // applied when the registers are filled.
     // row pitch of a staged gradient plane: 4*odd (mod 32) floats, so the 8 rows read by a quarter-warp hit 8 bank groups
-    static constexpr int GW = pitch_for(SHIFTED ? TW + 2 * R + XO + 3 : TW);
+    static constexpr int GW = pitch_for(SHIFTED ? TW + 4 : TW);
     static constexpr int GP = TH * GW;            // one plane tile, floats
     static constexpr int GS = D * GP;             // one gradient stage (D planes), floats
     static constexpr int THREADS = TH * NS * CG;
     static constexpr size_t SMEM = sizeof(float) * (FT + 2 * GS) + 8 * 3 + 1024;
     static_assert((FT * 4) % 128 == 0 && (GP * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
-    static_assert(((R2 * P2) / 4) % 2 == 1, "channel pitch must be 4*odd (mod 32)");
     static_assert(D % TIC == 0 && TH % 8 == 0 && kCB % CG == 0, "bad tile");
     static_assert(SMEM <= 227 * 1024, "tile does not fit in shared memory");
 };
@@ -280,16 +280,15 @@ __device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const fl
                                           float (&acc)[kBM][T::CN]) {
     float gv[TIC][kBM];
     if (SHIFTED) {
-        // the value for target x sits at column x - (x0 - R) + ti = s*8 + i + tii of the widened box: load the aligned
-        // window that covers [T0, T0 + TIC + 7) and pick the shifted 8 values per displacement
+        // plane tii was staged with its box origin at x0 - R + tii rounded down to a multiple of 4: the value for target
+        // column s*8 + i sits at box column s*8 + i + ((tii + XO) & 3)
 #pragma unroll
         for (int t = 0; t < TIC; ++t) {
             constexpr int LEN = kBM + 4;  // aligned window that covers 8 values starting anywhere inside a float4
-            const int a0 = (T0 + t + T::XO) & ~3;
             float w[LEN];
 #pragma unroll
             for (int i = 0; i < LEN; i += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + a0 + i);
+                const float4 v = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + i);
                 w[i] = v.x, w[i + 1] = v.y, w[i + 2] = v.z, w[i + 3] = v.w;
             }
 #pragma unroll
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED>::THREADS, 1)
 #pragma unroll 1
         for (int tii = 0; tii < D; ++tii) {
             if (SHIFTED)  // plane of displacement -t, rows shifted by tj here, columns shifted by ti at register fill
-                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0 - R - T::XO, y0 + tji - R,
+                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0 - R - T::XO + ((tii + T::XO) & ~3), y0 + tji - R,
                                  (2 * R - tji) * D + (2 * R - tii), b);
             else
                 ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0, y0, tji * D + tii, b);
@@ -443,7 +442,8 @@ int launch_bwd(const float* feat, const float* gO, float* gI, const CorrGeom& g,
 
 template <bool SHIFTED>
 int dispatch_bwd4(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
-    if (g.W > 32) return launch_bwd<4, 8, 8, 4, 9, SHIFTED>(feat, gO, gI, g, st);
+    // 8 x 32 tiles: 112 KB of shared memory per CTA -> two CTAs per SM, so one CTA's feature-tile load and epilogue
+    // overlap the other's arithmetic
     if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, SHIFTED>(feat, gO, gI, g, st);
     if (g.W > 8) return launch_bwd<4, 8, 2, 4, 9, SHIFTED>(feat, gO, gI, g, st);
     return launch_bwd<4, 8, 1, 4, 9, SHIFTED>(feat, gO, gI, g, st);

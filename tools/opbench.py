@@ -35,11 +35,20 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def cases(B, S):
+def cases(B, S, only=".*", dry=False):
     L = _lib.lib()
     out = []
 
+    def want(name):
+        return re.search(only, name) is not None
+
     def corr(tag, C, h, pad, md, s2):
+        names = [f"corr_fwd {tag} C{C} {h}x{h}", f"corr_bwd {tag} C{C} {h}x{h}"]
+        if dry:
+            out.extend((n, 0, 0, None) for n in names)
+            return
+        if not any(want(n) for n in names):
+            return
         f1 = torch.randn(B, C, h, h, device=DEV)
         f2 = torch.randn(B, C, h, h, device=DEV)
         D = 2 * (md // s2) + 1
@@ -57,6 +66,12 @@ def cases(B, S):
                                            stream())))
 
     def warp(tag, C, h, mode, want1, sigma):
+        names = [f"warp_fwd {tag} m{mode} C{C} {h}x{h}", f"warp_bwd {tag} m{mode} C{C} {h}x{h} gI1={int(want1)}"]
+        if dry:
+            out.extend((n, 0, 0, None) for n in names)
+            return
+        if not any(want(n) for n in names):
+            return
         x = torch.randn(B, C, h, h, device=DEV)
         # smooth flow (coarse random field upsampled 8x), like the decoder's upsampled flows -- not white noise
         fl = torch.nn.functional.interpolate(torch.randn(B, 2, max(h // 8, 1), max(h // 8, 1), device=DEV) * sigma,
@@ -75,6 +90,12 @@ def cases(B, S):
                                                stream())))
 
     def chnorm(C, h):
+        names = [f"chnorm_fwd C{C} {h}x{h}", f"chnorm_bwd C{C} {h}x{h}"]
+        if dry:
+            out.extend((n, 0, 0, None) for n in names)
+            return
+        if not any(want(n) for n in names):
+            return
         x = torch.randn(B, C, h, h, device=DEV)
         o = torch.empty(B, 1, h, h, device=DEV)
         go = torch.randn_like(o)
@@ -85,6 +106,12 @@ def cases(B, S):
                     lambda: L.ofr_chnorm_bwd(P(x), P(o), P(go), P(g), B, C, h, h, stream())))
 
     def loss(n):
+        names = [f"loss_fwd n{n} {S}x{S}", f"loss_bwd n{n} {S}x{S}"]
+        if dry:
+            out.extend((n, 0, 0, None) for n in names)
+            return
+        if not any(want(n) for n in names):
+            return
         fixed = torch.rand(B, 1, S, S, device=DEV)
         sizes = [S >> i for i in range(n)]
         flows = [torch.randn(B, 2, s, s, device=DEV) for s in sizes]
@@ -123,52 +150,76 @@ def cases(B, S):
     chnorm(1, S)
     chnorm(2, S)
     loss(7)
-    return out
+    return [c for c in out if want(c[0])]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=".*")
-    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=20, help="timed launches per case")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--json", default=None)
-    ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--single", action="store_true",
+                    help="one buffer set, L2 flushed before every launch, one event pair per launch (old method)")
     args = ap.parse_args()
     peak = 6556.2
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
     torch.manual_seed(6)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    names = [c[0] for c in cases(args.batch, args.size, only=args.only, dry=True)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV) if args.single else None
     rows = []
-    for name, nbytes, flops, fn in cases(args.batch, args.size):
-        if not re.search(args.only, name):
-            continue
+    for name in names:
+        # Rotating buffer sets: K independent copies of the case, together larger than the 126 MB L2, launched round
+        # robin back to back inside ONE event pair -> every launch sees cold inputs and the launch gap is amortised.
+        first = cases(args.batch, args.size, only="^" + re.escape(name) + "$")[0]
+        nbytes, flops = first[1], first[2]
+        K = 1 if args.single else max(2, min(8, (300 << 20) // max(nbytes, 1) + 1))
+        fns = [first[3]] + [cases(args.batch, args.size, only="^" + re.escape(name) + "$")[0][3] for _ in range(K - 1)]
         for _ in range(args.warmup):
-            rc = fn()
-            assert rc == 0, (name, rc)
+            for fn in fns:
+                rc = fn()
+                assert rc == 0, (name, rc)
         torch.cuda.synchronize()
-        ts = []
-        for _ in range(args.iters):
-            if not args.no_flush:
+        if args.single:
+            ts = []
+            for _ in range(args.iters):
                 flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
-        us = statistics.median(ts)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fns[0]()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            us = statistics.median(ts)
+        else:
+            rounds = max(1, (args.iters + K - 1) // K)
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _r in range(rounds):
+                    for fn in fns:
+                        fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3 / (rounds * K))
+            us = statistics.median(ts)
         gbs = nbytes / us / 1e3
-        row = dict(kernel=name, us=round(us, 2), min_us=round(min(ts), 2), MB=round(nbytes / 1e6, 2),
+        row = dict(kernel=name, us=round(us, 2), min_us=round(min(ts), 2), MB=round(nbytes / 1e6, 2), copies=K,
                    gbs=round(gbs, 1), hbm_frac=round(gbs / peak, 4), tflops=round(flops / us / 1e6, 2))
         rows.append(row)
         print(f"{name:44s} {us:9.1f} us  {nbytes/1e6:8.1f} MB {gbs:8.1f} GB/s  {100*gbs/peak:5.1f}% HBM  "
               f"{row['tflops']:6.2f} TFLOP/s", flush=True)
+        del fns, first
+        torch.cuda.empty_cache()
     if args.json:
-        json.dump(dict(peak_hbm_gbs=peak, batch=args.batch, size=args.size, rows=rows), open(args.json, "w"), indent=1)
+        json.dump(dict(peak_hbm_gbs=peak, batch=args.batch, size=args.size,
+                       method="single+flush" if args.single else "rotating buffer sets > L2, back-to-back launches",
+                       rows=rows), open(args.json, "w"), indent=1)
 
 
 if __name__ == "__main__":
