@@ -17,11 +17,11 @@
 // Backward : gI2 (flow) is a per-source gather + analytic derivative.
 //            gI1 (image) is the adjoint scatter.  Upstream used float atomicAdd (non-deterministic); here it is a
 //            per-target gather in a data-defined order (north-star rule 3):
-//              1. resample_prep_kernel writes one 16-byte record per source pixel {key, (x0,y0), wx1, wy1} in source-tile
+//              1. resample_prep_kernel writes one 16-byte record per source pixel {offset, (x0,y0), wx1, wy1} in source-tile
 //                 major order and the bounding box of the footprint cells of every 8 x 32 source tile;
 //              2. resample_bwd_fused_kernel: one CTA per 8 x 32 tile of TARGETS.  It finds the source tiles whose
 //                 bounding box touches the tile (ascending), bins their records by footprint cell in SHARED memory
-//                 (integer atomics only: counts and slots are order independent once each cell is sorted by key), and
+//                 (integer atomics only: counts and slots are order independent once each cell is sorted by source offset), and
 //                 every target thread then walks its <= 4 cells in a fixed order, gathering gO for 16 channels at a
 //                 time.  The same thread also forms the flow gradient of the source pixel at its own position, so gO
 //                 and in1 are read once.  When the channels are split over several CTAs (small maps), the CTAs of one
@@ -135,40 +135,45 @@ __device__ __forceinline__ float fetch(const float* __restrict__ img, int off) {
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int kFwdThreads = 256;
 constexpr int kFwdChunk = 8;  // channels per blockIdx.z slice
+constexpr int kPX = 4;        // pixels per thread, stacked in a column
 
-// blockDim = (bx, by) with bx * by = 256; thread = PX consecutive pixels of one row; blockIdx.z = image * nchunks + chunk
-template <int MODE, int PX>
-__global__ void __launch_bounds__(kFwdThreads) resample_fwd_kernel(const float* __restrict__ in1,
-                                                                   const float* __restrict__ flow,
-                                                                   float* __restrict__ out, WarpGeom g, int nchunks) {
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= g.Wf || y >= g.Hf) return;
+// blockDim = (bx, by), bx * by = 256, bx <= 32: the lanes of a warp are CONSECUTIVE pixels of 32/bx rows, so every flow
+// load, tap gather and output store of a warp covers whole runs of consecutive pixels (1-2 cache lines per request for
+// smooth flows; four pixels per thread along x would spread every request over four lines and make the L1 tag stage the
+// bottleneck).  A thread owns kPX vertically adjacent pixels: rows y0 .. y0+kPX-1, whose tap rows overlap in L1.
+// blockIdx.z = image * nchunks + channel chunk.
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const float* __restrict__ in1,
+                                                                      const float* __restrict__ flow,
+                                                                      float* __restrict__ out, WarpGeom g, int nchunks) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
+    if (x >= g.Wf || y0 >= g.Hf) return;
     const int hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
-    const int rem = y * g.Wf + x;
+    const int rem = y0 * g.Wf + x;
+    bool ok[kPX];
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) ok[k] = y0 + k < g.Hf;
     for (int z = blockIdx.z; z < g.B * nchunks; z += gridDim.z) {
         const int b = z / nchunks, chunk = z - b * nchunks;
         const int c0 = chunk * kFwdChunk, c1 = min(c0 + kFwdChunk, g.C);
         const float* fu = flow + (size_t)b * 2 * hwf + rem;
-        float u[PX], v[PX];
-        if (PX == 4) {
-            const float4 a = ofr::ldg4(fu), c = ofr::ldg4(fu + hwf);
-            u[0] = a.x, u[1 % PX] = a.y, u[2 % PX] = a.z, u[3 % PX] = a.w;
-            v[0] = c.x, v[1 % PX] = c.y, v[2 % PX] = c.z, v[3 % PX] = c.w;
-        } else {
-            u[0] = __ldg(fu);
-            v[0] = __ldg(fu + hwf);
-        }
-        TapOff t[PX];
-        float w00[PX], w01[PX], w10[PX], w11[PX];
-        bool live[PX];
+        float u[kPX], v[kPX];
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            const Samp s = make_samp<MODE>(x + k, y, u[k], v[k], g);
+        for (int k = 0; k < kPX; ++k) {
+            u[k] = ok[k] ? __ldg(fu + k * g.Wf) : 0.f;
+            v[k] = ok[k] ? __ldg(fu + hwf + k * g.Wf) : 0.f;
+        }
+        TapOff t[kPX];
+        float w00[kPX], w01[kPX], w10[kPX], w11[kPX];
+        bool live[kPX];
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) {
+            const Samp s = make_samp<MODE>(x, y0 + k, u[k], v[k], g);
             live[k] = s.live;
             if (MODE == OFR_WARP_FLOWNET2_NEAREST) {  // nearest tap: floor(x + u + 0.5), clamped
-                const float xn = floorf(__fadd_rn(__fadd_rn((float)(x + k), u[k]), 0.5f));
-                const float yn = floorf(__fadd_rn(__fadd_rn((float)y, v[k]), 0.5f));
+                const float xn = floorf(__fadd_rn(__fadd_rn((float)x, u[k]), 0.5f));
+                const float yn = floorf(__fadd_rn(__fadd_rn((float)(y0 + k), v[k]), 0.5f));
                 const int xi = min(max(safe_floor_int(xn, g.Win), 0), g.Win - 1);
                 const int yi = min(max(safe_floor_int(yn, g.Hin), 0), g.Hin - 1);
                 t[k].tl = yi * g.Win + xi;
@@ -182,10 +187,11 @@ __global__ void __launch_bounds__(kFwdThreads) resample_fwd_kernel(const float* 
         }
         const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
         float* o = out + ((size_t)b * g.C + c0) * hwf + rem;
+#pragma unroll 2
         for (int c = c0; c < c1; ++c, img += hwi, o += hwf) {
-            float r[PX];
+            float r[kPX];
 #pragma unroll
-            for (int k = 0; k < PX; ++k) {
+            for (int k = 0; k < kPX; ++k) {
                 if (MODE == OFR_WARP_FLOWNET2_NEAREST) {
                     r[k] = __ldg(img + t[k].tl);
                 } else {
@@ -196,10 +202,9 @@ __global__ void __launch_bounds__(kFwdThreads) resample_fwd_kernel(const float* 
                     r[k] = live[k] ? acc : 0.f;
                 }
             }
-            if (PX == 4)
-                ofr::stcs4(o, make_float4(r[0], r[1 % PX], r[2 % PX], r[3 % PX]));
-            else
-                o[0] = r[0];
+#pragma unroll
+            for (int k = 0; k < kPX; ++k)
+                if (ok[k]) __stcs(o + k * g.Wf, r[k]);
         }
     }
 }
@@ -207,66 +212,59 @@ __global__ void __launch_bounds__(kFwdThreads) resample_fwd_kernel(const float* 
 // ------------------------------------------------------------------------------------------------ backward: flow only
 // gI2 only (the image needs no gradient: opticalFlowReg.stn on the moving image, FlowNet2's Resample2d on the input
 // images).  Same thread mapping as the forward; channels looped in the thread.
-template <int MODE, int PX>
-__global__ void __launch_bounds__(kFwdThreads) resample_bwd_flow_kernel(const float* __restrict__ in1,
-                                                                        const float* __restrict__ flow,
-                                                                        const float* __restrict__ gO,
-                                                                        float* __restrict__ gI2, WarpGeom g, float sx,
-                                                                        float sy) {
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= g.Wf || y >= g.Hf) return;
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const float* __restrict__ in1,
+                                                                           const float* __restrict__ flow,
+                                                                           const float* __restrict__ gO,
+                                                                           float* __restrict__ gI2, WarpGeom g,
+                                                                           float sx, float sy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
+    if (x >= g.Wf || y0 >= g.Hf) return;
     const int hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
-    const int rem = y * g.Wf + x;
+    const int rem = y0 * g.Wf + x;
+    bool ok[kPX];
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) ok[k] = y0 + k < g.Hf;
     for (int b = blockIdx.z; b < g.B; b += gridDim.z) {
         const float* fu = flow + (size_t)b * 2 * hwf + rem;
-        float u[PX], v[PX];
-        if (PX == 4) {
-            const float4 a = ofr::ldg4(fu), c = ofr::ldg4(fu + hwf);
-            u[0] = a.x, u[1 % PX] = a.y, u[2 % PX] = a.z, u[3 % PX] = a.w;
-            v[0] = c.x, v[1 % PX] = c.y, v[2 % PX] = c.z, v[3 % PX] = c.w;
-        } else {
-            u[0] = __ldg(fu);
-            v[0] = __ldg(fu + hwf);
-        }
-        TapOff t[PX];
-        Samp s[PX];
+        float u[kPX], v[kPX];
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            s[k] = make_samp<MODE>(x + k, y, u[k], v[k], g);
+        for (int k = 0; k < kPX; ++k) {
+            u[k] = ok[k] ? __ldg(fu + k * g.Wf) : 0.f;
+            v[k] = ok[k] ? __ldg(fu + hwf + k * g.Wf) : 0.f;
+        }
+        TapOff t[kPX];
+        Samp s[kPX];
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) {
+            s[k] = make_samp<MODE>(x, y0 + k, u[k], v[k], g);
             t[k] = tap_offsets<MODE>(s[k].x0, s[k].y0, g.Hin, g.Win);
-            if (!s[k].live) t[k].tl = t[k].tr = t[k].bl = t[k].br = -1;
+            if (!s[k].live || !ok[k]) t[k].tl = t[k].tr = t[k].bl = t[k].br = -1;
         }
-        float ax[PX], ay[PX];
+        float ax[kPX], ay[kPX];
 #pragma unroll
-        for (int k = 0; k < PX; ++k) ax[k] = ay[k] = 0.f;
+        for (int k = 0; k < kPX; ++k) ax[k] = ay[k] = 0.f;
         const float* img = in1 + (size_t)b * g.C * hwi;
         const float* gp = gO + (size_t)b * g.C * hwf + rem;
         for (int c = 0; c < g.C; ++c, img += hwi, gp += hwf) {
-            float go[PX];
-            if (PX == 4) {
-                const float4 q = ofr::ldg4(gp);
-                go[0] = q.x, go[1 % PX] = q.y, go[2 % PX] = q.z, go[3 % PX] = q.w;
-            } else {
-                go[0] = __ldg(gp);
-            }
 #pragma unroll
-            for (int k = 0; k < PX; ++k) {
+            for (int k = 0; k < kPX; ++k) {
+                const float go = ok[k] ? __ldg(gp + k * g.Wf) : 0.f;
                 const float tl = fetch(img, t[k].tl), tr = fetch(img, t[k].tr);
                 const float bl = fetch(img, t[k].bl), br = fetch(img, t[k].br);
                 // d out / d ix = wy0*(TR-TL) + wy1*(BR-BL);  d out / d iy = wx0*(BL-TL) + wx1*(BR-TR)
-                ax[k] = fmaf(go[k], fmaf(s[k].wy1, br - bl, s[k].wy0 * (tr - tl)), ax[k]);
-                ay[k] = fmaf(go[k], fmaf(s[k].wx1, br - tr, s[k].wx0 * (bl - tl)), ay[k]);
+                ax[k] = fmaf(go, fmaf(s[k].wy1, br - bl, s[k].wy0 * (tr - tl)), ax[k]);
+                ay[k] = fmaf(go, fmaf(s[k].wx1, br - tr, s[k].wx0 * (bl - tl)), ay[k]);
             }
         }
         float* o = gI2 + (size_t)b * 2 * hwf + rem;
-        if (PX == 4) {
-            ofr::stcs4(o, make_float4(ax[0] * sx, ax[1 % PX] * sx, ax[2 % PX] * sx, ax[3 % PX] * sx));
-            ofr::stcs4(o + hwf, make_float4(ay[0] * sy, ay[1 % PX] * sy, ay[2 % PX] * sy, ay[3 % PX] * sy));
-        } else {
-            o[0] = ax[0] * sx;
-            o[hwf] = ay[0] * sy;
-        }
+#pragma unroll
+        for (int k = 0; k < kPX; ++k)
+            if (ok[k]) {
+                __stcs(o + k * g.Wf, ax[k] * sx);
+                __stcs(o + hwf + k * g.Wf, ay[k] * sy);
+            }
     }
 }
 
@@ -297,8 +295,8 @@ __device__ __forceinline__ void cell_of(int x0, int y0, const WarpGeom& g, int& 
     }
 }
 
-// One record per source pixel, stored source-tile major: recs[(image, tile)][256].  {key, packed (x0,y0) or -1 when the
-// source reaches no target, wx1, wy1}; key = tile * 256 + index in tile: the canonical visiting order.
+// One record per source pixel, stored source-tile major: recs[(image, tile)][256].  {source offset inside a plane,
+// packed (x0,y0) or -1 when the source reaches no target, wx1, wy1}.
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads) resample_prep_kernel(const float* __restrict__ flow,
                                                                      int4* __restrict__ recs, int4* __restrict__ bbox,
@@ -307,7 +305,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_prep_kernel(const float
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
     const int sx = blockIdx.x * kTX + lx, sy = blockIdx.y * kTY + ly, b = blockIdx.z;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x, nst = gridDim.x * gridDim.y;
-    int4 rec = make_int4(tile * kTileThreads + tid, -1, 0, 0);
+    int4 rec = make_int4(sy * g.Wf + sx, -1, 0, 0);
     int kx0 = INT_MAX, kx1 = INT_MIN, ky0 = INT_MAX, ky1 = INT_MIN;
     if (sx < g.Wf && sy < g.Hf) {
         const int hwf = g.Hf * g.Wf;
@@ -350,7 +348,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_prep_kernel(const float
 
 // blockIdx = (target tile x, target tile y, image * csplit + split); launched with cluster dims (1, 1, csplit).
 template <int MODE, bool WANT1, bool WANT2>
-__global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
+__global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
     const float* __restrict__ in1, const float* __restrict__ gO, const int4* __restrict__ recs,
     const int4* __restrict__ bbox, float* __restrict__ gI1, float* __restrict__ gI2, WarpGeom g, int stx, int sty,
     int csplit, int chunks_per_cta, float gsx, float gsy) {
@@ -427,12 +425,6 @@ __global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
         if (xr == tx && yb == ty) acc = __fadd_rn(acc, __fmul_rn(wx1, wy1));
         return acc;
     };
-    // element offset of the source with this key inside one plane of gO
-    auto src_of = [&](int key) {
-        const int t = key / kTileThreads, l = key - t * kTileThreads;
-        const int tyi = t / stx, txi = t - tyi * stx;
-        return (tyi * kTY + (l >> 5)) * g.Wf + txi * kTX + (l & 31);
-    };
 
     int total = 0;
     int start[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0}, mycell[4];
@@ -482,7 +474,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
             const int bin = bin_of(r);
             if (bin >= 0) srec[coff[bin] + atomicAdd(&ccount[bin], 1)] = r;
         });
-        // canonical order inside every cell: ascending key (one thread per cell, insertion sort in shared memory)
+        // canonical order inside every cell: ascending source offset (one thread per cell, insertion sort in shared memory)
         for (int cell = tid; cell < kCells; cell += kTileThreads) {
             const int o = coff[cell], n = coff[cell + 1] - o;
             for (int i = 1; i < n; ++i) {
@@ -503,12 +495,12 @@ __global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
         }
         s1 = cnt[0], s2 = s1 + cnt[1], s3 = s2 + cnt[2], tot_e = s3 + cnt[3];
     }
-    // e-th record of this target in visiting order (cells TL, TR, BL, BR; ascending key inside a cell)
+    // e-th record of this target in visiting order (cells TL, TR, BL, BR; ascending source offset inside a cell)
     auto entry = [&](int e, int& src, float& w) {
         const int q = (e >= s1) + (e >= s2) + (e >= s3);  // no dynamically indexed arrays
         const int base = q == 0 ? start[0] : q == 1 ? start[1] - s1 : q == 2 ? start[2] - s2 : start[3] - s3;
         const int4 r = srec[base + e];
-        src = src_of(r.x);
+        src = r.x;
         w = weight_of(r);
     };
     if (staged) {  // decode the first kListCap records once; the channel sweeps then only gather + FMA
@@ -547,14 +539,14 @@ __global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
 #pragma unroll
             for (int k = 0; k < kChunk; ++k) acc[k] = 0.f;
             auto gather = [&](int src, float w) {
-                const float* gp = go + src;
+                const float* gp = go + src;  // bumped plane by plane: one IMAD.WIDE per load
                 float gv[kChunk];
                 if (nc == kChunk) {  // full chunk: no per-channel predicates
 #pragma unroll
-                    for (int k = 0; k < kChunk; ++k) gv[k] = __ldg(gp + (size_t)k * hwf);
+                    for (int k = 0; k < kChunk; ++k, gp += hwf) gv[k] = __ldg(gp);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < kChunk; ++k) gv[k] = (k < nc) ? __ldg(gp + (size_t)k * hwf) : 0.f;
+                    for (int k = 0; k < kChunk; ++k, gp += hwf) gv[k] = (k < nc) ? __ldg(gp) : 0.f;
                 }
 #pragma unroll
                 for (int k = 0; k < kChunk; ++k) acc[k] = fmaf(w, gv[k], acc[k]);
@@ -583,7 +575,7 @@ __global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
                         __syncthreads();
                         for (int j = 0; j < kTileThreads; ++j) {
                             const int4 rj = srec[j];
-                            if (bin_of(rj) == want) gather(src_of(rj.x), weight_of(rj));
+                            if (bin_of(rj) == want) gather(rj.x, weight_of(rj));
                         }
                     });
                 }
@@ -591,17 +583,21 @@ __global__ void __launch_bounds__(kTileThreads) resample_bwd_fused_kernel(
             if (live) {
                 float* o = gI1 + ((size_t)b * g.C + c0) * hwi + ty * g.Win + tx;
 #pragma unroll
-                for (int k = 0; k < kChunk; ++k)
-                    if (k < nc) o[(size_t)k * hwi] = acc[k];
+                for (int k = 0; k < kChunk; ++k, o += hwi)
+                    if (k < nc) *o = acc[k];
             }
         }
         if (WANT2 && live) {
+            // four tap pointers and the own-pixel pointer, bumped plane by plane (invalid taps never dereferenced)
             const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
+            const float *ptl = img + max(ot.tl, 0), *ptr = img + max(ot.tr, 0);
+            const float *pbl = img + max(ot.bl, 0), *pbr = img + max(ot.br, 0);
+            const float* pg = go + orem;
 #pragma unroll 4
-            for (int k = 0; k < nc; ++k, img += hwi) {
-                const float gv = __ldg(go + (size_t)k * hwf + orem);
-                const float tl = fetch(img, ot.tl), tr = fetch(img, ot.tr);
-                const float bl = fetch(img, ot.bl), br = fetch(img, ot.br);
+            for (int k = 0; k < nc; ++k, ptl += hwi, ptr += hwi, pbl += hwi, pbr += hwi, pg += hwf) {
+                const float gv = __ldg(pg);
+                const float tl = ot.tl >= 0 ? __ldg(ptl) : 0.f, tr = ot.tr >= 0 ? __ldg(ptr) : 0.f;
+                const float bl = ot.bl >= 0 ? __ldg(pbl) : 0.f, br = ot.br >= 0 ? __ldg(pbr) : 0.f;
                 ax = fmaf(gv, fmaf(owy1, br - bl, owy0 * (tr - tl)), ax);
                 ay = fmaf(gv, fmaf(owx1, br - tr, owx0 * (bl - tl)), ay);
             }
@@ -654,7 +650,7 @@ WsLayout ws_layout(int B, int Hf, int Wf) {
 
 bool geom_ok(int B, int C, int Hin, int Win, int Hf, int Wf) {
     if (B <= 0 || C <= 0 || Hin <= 0 || Win <= 0 || Hf <= 0 || Wf <= 0) return false;
-    // index arithmetic inside one image plane is 32-bit; keys (tile * 256 + lane) too
+    // index arithmetic inside one image plane is 32-bit
     if ((long long)Hf * Wf >= (1ll << 30) || (long long)Hin * Win >= (1ll << 30)) return false;
     if (Hin > 32000 || Win > 32000 || Hf > 32000 || Wf > 32000) return false;  // (x0, y0) are packed in 16 bits each
     if (B > 65535) return false;
@@ -669,27 +665,23 @@ WarpGeom make_geom(int B, int C, int Hin, int Win, int Hf, int Wf) {
     return g;
 }
 
-// (bx, by) with bx * by = 256 threads: bx = the smallest power of two covering a row of `items`, at most 64
-void block_shape(int items, dim3& block, int& bx) {
-    bx = 1;
-    while (bx < items && bx < 64) bx <<= 1;
-    block = dim3(bx, kFwdThreads / bx);
+// (bx, by) with bx * by = 256 threads: bx = the smallest power of two covering a row, at most 32 (one warp = whole runs
+// of consecutive pixels); a CTA covers by * kPX rows
+void block_shape(int W, int H, dim3& block, dim3& grid, unsigned gz) {
+    int bx = 8;
+    while (bx < W && bx < 32) bx <<= 1;
+    const int by = kFwdThreads / bx;
+    block = dim3(bx, by);
+    grid = dim3((W + bx - 1) / bx, (H + by * kPX - 1) / (by * kPX), gz);
 }
 
 template <int MODE>
 int launch_fwd(const float* in1, const float* flow, float* out, const WarpGeom& g, cudaStream_t st) {
     const int nchunks = (g.C + kFwdChunk - 1) / kFwdChunk;
-    const bool vec = (g.Wf % 4 == 0) && ofr::aligned16(flow) && ofr::aligned16(out);
-    const int items = vec ? g.Wf / 4 : g.Wf;
-    dim3 block;
-    int bx;
-    block_shape(items, block, bx);
     const long long gz = (long long)g.B * nchunks;
-    dim3 grid((items + bx - 1) / bx, (g.Hf + block.y - 1) / block.y, (unsigned)(gz < 65535 ? gz : 65535));
-    if (vec)
-        resample_fwd_kernel<MODE, 4><<<grid, block, 0, st>>>(in1, flow, out, g, nchunks);
-    else
-        resample_fwd_kernel<MODE, 1><<<grid, block, 0, st>>>(in1, flow, out, g, nchunks);
+    dim3 block, grid;
+    block_shape(g.Wf, g.Hf, block, grid, (unsigned)(gz < 65535 ? gz : 65535));
+    resample_fwd_kernel<MODE><<<grid, block, 0, st>>>(in1, flow, out, g, nchunks);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
@@ -697,16 +689,9 @@ int launch_fwd(const float* in1, const float* flow, float* out, const WarpGeom& 
 template <int MODE>
 int launch_flow_only(const float* in1, const float* flow, const float* gO, float* gI2, const WarpGeom& g, float sx,
                      float sy, cudaStream_t st) {
-    const bool vec = (g.Wf % 4 == 0) && ofr::aligned16(flow) && ofr::aligned16(gO) && ofr::aligned16(gI2);
-    const int items = vec ? g.Wf / 4 : g.Wf;
-    dim3 block;
-    int bx;
-    block_shape(items, block, bx);
-    dim3 grid((items + bx - 1) / bx, (g.Hf + block.y - 1) / block.y, (unsigned)g.B);
-    if (vec)
-        resample_bwd_flow_kernel<MODE, 4><<<grid, block, 0, st>>>(in1, flow, gO, gI2, g, sx, sy);
-    else
-        resample_bwd_flow_kernel<MODE, 1><<<grid, block, 0, st>>>(in1, flow, gO, gI2, g, sx, sy);
+    dim3 block, grid;
+    block_shape(g.Wf, g.Hf, block, grid, (unsigned)g.B);
+    resample_bwd_flow_kernel<MODE><<<grid, block, 0, st>>>(in1, flow, gO, gI2, g, sx, sy);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
