@@ -24,6 +24,8 @@
 //                                                                  its rows shifted by tj; the x shift is applied
 //                                                                  when the registers are filled)
 //   No atomics, fixed summation order -> bitwise reproducible.
+#include <cstdlib>
+
 #include "corr_internal.cuh"
 #include "tma.cuh"
 
@@ -56,25 +58,28 @@ struct FwdT {
     static constexpr int TJG = (D + 7) / 8;
     static constexpr int T1 = 8 * TH * NS;
     static constexpr int THREADS = kNine ? D * TH * NS : 8 * TJG * TH * NS;
-    static constexpr int OP = TH * TW;        // one output plane tile, floats
-    static constexpr int OS = D * OP;         // epilogue staging buffer: the D planes {tj*D + j} of one j
-    static constexpr size_t SMEM = sizeof(float) * (STAGE * NST + 2 * OS) + 8 * NST + 1024;
-    static_assert((F1 * 4) % 128 == 0 && (F2 * 4) % 128 == 0 && (OP * 4) % 128 == 0,
-                  "TMA sources / destinations must stay 128-byte aligned");
+    static constexpr int NWARPS = (THREADS + 31) / 32;
+    static constexpr int WSTAGE = 32 * (M + 4) * 4;  // bytes of one per-warp epilogue staging buffer (covers both lane layouts)
+    static constexpr int CPR = NS * M / 4;           // 16-byte chunks per run
+    static constexpr int EPI = M / 4;                // chunks every lane writes back per step: 32/NS runs * CPR / 32 lanes
+    static constexpr size_t SMEM = sizeof(float) * (STAGE * NST) + (size_t)NWARPS * 2 * WSTAGE + 8 * NST + 1024;
+    static_assert(32 / NS * (NS * M + 4) <= 32 * (M + 4) && TH * (NS * M + 4) <= 32 * (M + 4) && TH * NS <= 32 &&
+                      NS <= 4 && (NS & (NS - 1)) == 0 && (TH * NS) % 4 == 0 && T1 % 32 == 0,
+                  "staging layout");
+    static_assert((F1 * 4) % 128 == 0 && (F2 * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(M % 4 == 0 && THREADS <= 1024, "bad tile");
 };
 
 template <int R, int M, int TH, int NS, int CK, int NST>
 __global__ void __maxnreg__(224)
     corr_fwd_tma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                        const __grid_constant__ CUtensorMap mapO, CorrGeom g, int tiles_x, int tiles_y) {
+                        float* __restrict__ out, CorrGeom g, int tiles_x, int tiles_y) {
     using T = FwdT<R, M, TH, NS, CK, NST>;
     constexpr int D = T::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // round the base up to 1024 B with an offset (not an integer cast) so the pointer stays in the shared window: LDS, not LD
     float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
-    float* ostage = smem + T::STAGE * NST;  // [2][D][TH][TW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + 2 * T::OS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::STAGE * NST + T::NWARPS * (2 * T::WSTAGE / 4));
 
     const int tid = threadIdx.x;
     int tj, s, row;
@@ -100,6 +105,22 @@ __global__ void __maxnreg__(224)
     const bool active = tj < D;
     const int tjc = active ? tj : D - 1;  // idle lanes read valid shared memory and discard the result
 
+    // epilogue staging: one private area per warp, two buffers of WSTAGE bytes, organised in runs of NS*M pixels
+    // (+16 bytes of padding so the 8 tj lanes of a quarter-warp store to 8 different bank groups).
+    //   regular warps : lanes = 8 tj x 4 (strip,row) pairs; run r = (tj = tj_base + (r & 7), row = row_base + (r >> 3))
+    //   tj = D-1 warp of the D = 9 layout : lanes = rows x strips; run r = row r
+    const int lane = tid & 31;
+    const bool grouped = !(T::kNine && tid >= T::T1);
+    const int qb = (tid >> 5) * 4;  // first (strip,row) pair of the warp
+    const int tj_base = T::kNine ? 0 : (qb / (TH * NS)) * 8;
+    const int row_base = T::kNine ? qb / NS : (qb % (TH * NS)) / NS;
+    const int nruns = grouped ? 32 / NS : TH;
+    const int slot = grouped ? (((lane & 7) + 8 * ((lane >> 3) / NS)) * (NS * M + 4) + ((lane >> 3) % NS) * M)
+                             : row * (NS * M + 4) + s * M;
+    float* wstage = smem + T::STAGE * NST + (tid >> 5) * (2 * T::WSTAGE / 4);
+    const unsigned wmask = __activemask();
+    int jcount = 0;
+
     const int nchunks = (g.C + CK - 1) / CK;
     const int ntiles = tiles_x * tiles_y * g.B;
     const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -124,7 +145,6 @@ __global__ void __maxnreg__(224)
     if (tid == 0) {
         ofr::tma_prefetch_desc(&map1);
         ofr::tma_prefetch_desc(&map2);
-        ofr::tma_prefetch_desc(&mapO);
         for (int i = 0; i < NST; ++i) ofr::mbar_init(&bars[i], 1);
         ofr::mbar_fence_init();
     }
@@ -168,52 +188,45 @@ __global__ void __maxnreg__(224)
             issue(q + NST);
         }
         if (++ck == nchunks) {
-            // Tile finished.  Epilogue through shared memory and TMA stores: for each x-displacement j the CTA stages
-            // the D planes {tj*D + j} (dense TH x TW boxes) and one thread issues D asynchronous tensor stores; the
-            // stores drain while the next tile is being computed, write whole 128-byte lines, and clip rows / columns
-            // outside the image by themselves.  Two staging buffers alternate.
+            // Tile finished.  Warp-private epilogue (no CTA barrier, so warps drift apart and overlap their phases):
+            // for each x-displacement j the lanes park their M-pixel runs in the warp's staging buffer so that the NS
+            // strips of one (plane, row) are contiguous, the warp reads the buffer back as whole 16-byte chunks in run
+            // order, and every STG.128 of the warp then covers whole 128-byte lines (evict-first).  Two staging
+            // buffers alternate, so one __syncwarp per step orders everything.
+            // (Register -> global STG.128 straight from the accumulator layout scatters every store over 16-32 sectors
+            // and cost 36 % of the kernel; a CTA-wide staged TMA-store epilogue cost more in barriers; 256-byte bulk
+            // copies per run were slower than both.)
             int x0, y0, b;
             tile_origin(tile_k, x0, y0, b);
-            const int rot = tj & 3;  // 16-byte chunk rotation: halves the bank conflicts of the 8 tj lanes of a quarter-warp
+            const size_t hw = (size_t)g.Hout * g.Wout;
+            float* dst[T::EPI];
+            const float* src[T::EPI];
+#pragma unroll
+            for (int k = 0; k < T::EPI; ++k) {
+                const int idx = k * (grouped ? 32 : TH * NS) + lane, r = idx / T::CPR, c = idx % T::CPR;
+                const int tj_r = grouped ? tj_base + (r & 7) : D - 1, row_r = grouped ? row_base + (r >> 3) : r;
+                const int y = y0 + row_r, x = x0 + c * 4;
+                const bool ok = r < nruns && tj_r < D && y < g.Hout && x < g.Wout;
+                dst[k] = ok ? out + ((size_t)b * D * D + (size_t)tj_r * D) * hw + (size_t)y * g.Wout + x : nullptr;
+                src[k] = wstage + r * (NS * M + 4) + c * 4;
+            }
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                float* buf = ostage + ((j + tile_k * D) & 1) * T::OS;  // D is odd: keep consecutive groups alternating
-                if (tid == 0) ofr::tma_store_wait_read<1>();  // the group that last read this buffer is done with it
-                __syncthreads();
-                if (active) {
-                    float* dst = buf + tj * T::OP + row * T::TW + s * M;
-                    if (M >= 16) {
+                const int boff = (jcount & 1) * (T::WSTAGE / 4);
+                float* buf = wstage + boff + slot;
 #pragma unroll
-                        for (int i0 = 0; i0 < M; i0 += 16) {
-                            float4 c[4];
+                for (int i = 0; i < M; i += 4)
+                    *reinterpret_cast<float4*>(buf + i) = make_float4(acc[i][j] * g.scale, acc[i + 1][j] * g.scale,
+                                                                      acc[i + 2][j] * g.scale, acc[i + 3][j] * g.scale);
+                __syncwarp(wmask);
 #pragma unroll
-                            for (int qd = 0; qd < 4; ++qd) {
-                                const int i = i0 + 4 * qd;
-                                c[qd] = make_float4(acc[i % M][j] * g.scale, acc[(i + 1) % M][j] * g.scale,
-                                                    acc[(i + 2) % M][j] * g.scale, acc[(i + 3) % M][j] * g.scale);
-                            }
-                            // rotate the four chunks left by `rot` with selects (registers cannot be indexed dynamically)
-#pragma unroll
-                            for (int qd = 0; qd < 4; ++qd) {
-                                const float4 p0 = c[qd], p1 = c[(qd + 1) & 3], p2 = c[(qd + 2) & 3], p3 = c[(qd + 3) & 3];
-                                const float4 d = rot == 0 ? p0 : rot == 1 ? p1 : rot == 2 ? p2 : p3;
-                                *reinterpret_cast<float4*>(dst + i0 + 4 * ((qd + rot) & 3)) = d;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < M; i += 4)
-                            *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i][j] * g.scale, acc[i + 1][j] * g.scale,
-                                                                              acc[i + 2][j] * g.scale, acc[i + 3][j] * g.scale);
+                for (int k = 0; k < T::EPI; ++k) {
+                    if (dst[k]) {
+                        __stcs(reinterpret_cast<float4*>(dst[k]), *reinterpret_cast<const float4*>(src[k] + boff));
+                        dst[k] += hw;
                     }
                 }
-                ofr::fence_proxy_async();  // make the generic-proxy writes visible to the TMA engine
-                __syncthreads();
-                if (tid == 0) {
-#pragma unroll 1
-                    for (int t = 0; t < D; ++t) ofr::tma_store_4d(&mapO, buf + t * T::OP, x0, y0, t * D + j, b);
-                    ofr::tma_store_commit();
-                }
+                ++jcount;
             }
 #pragma unroll
             for (int i = 0; i < M; ++i)
@@ -223,16 +236,14 @@ __global__ void __maxnreg__(224)
             ++tile_k;
         }
     }
-    if (tid == 0) ofr::tma_store_wait_all<0>();  // shared memory must outlive the stores that read it
 }
 
 template <int R, int M, int TH, int NS, int CK, int NST>
 int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
     using T = FwdT<R, M, TH, NS, CK, NST>;
-    CUtensorMap m1, m2, mo;
+    CUtensorMap m1, m2;
     if (!ofr::make_tmap_nchw(&m1, f1, g.B, g.C, g.H, g.W, T::P1, TH, CK)) return OFR_ENOTSUP;
     if (!ofr::make_tmap_nchw(&m2, f2, g.B, g.C, g.H, g.W, T::P2, T::R2, CK)) return OFR_ENOTSUP;
-    if (!ofr::make_tmap_nchw(&mo, out, g.B, T::D * T::D, g.Hout, g.Wout, T::TW, TH, 1)) return OFR_ENOTSUP;
     auto kern = corr_fwd_tma_kernel<R, M, TH, NS, CK, NST>;
     OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
     const int tiles_x = (g.Wout + T::TW - 1) / T::TW, tiles_y = (g.Hout + TH - 1) / TH;
@@ -240,7 +251,7 @@ int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, 
     const int ctas_per_sm = (int)(227 * 1024 / T::SMEM) < 1 ? 1 : (int)(227 * 1024 / T::SMEM);
     long long grid = (long long)ofr::sm_count() * (ctas_per_sm > 4 ? 4 : ctas_per_sm);
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, T::THREADS, T::SMEM, st>>>(m1, m2, mo, g, tiles_x, tiles_y);
+    kern<<<(unsigned)grid, T::THREADS, T::SMEM, st>>>(m1, m2, out, g, tiles_x, tiles_y);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
@@ -462,7 +473,12 @@ int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g
     if (applicable(g, 4, f1, f2, out)) {
         // 7 rows: 7 warps own tj = 0..7 and one warp owns tj = 8 -> 8 warps; a 9-warp CTA would be allocated registers
         // for 12 warps and could not keep the 144 accumulators of the 16-pixel strip
-        if (g.W > 32) return launch_fwd<4, 16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
+        if (g.W > 32) {
+            static const int v = getenv("OFR_FWD_V") ? atoi(getenv("OFR_FWD_V")) : 0;  // tuning switch (development only)
+            if (v == 2) return launch_fwd<4, 16, 8, 2, 8, 2>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads, 2 CTAs/SM
+            if (v == 3) return launch_fwd<4, 8, 8, 4, 8, 3>(f1, f2, out, g, st);    // 8 x 32 tile, 8-px strips, 288 threads
+            return launch_fwd<4, 16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
+        }
         if (g.W > 16) return launch_fwd<4, 16, 8, 2, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads
         if (g.W > 8) return launch_fwd<4, 16, 8, 1, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile,  72 threads
         return launch_fwd<4, 8, 8, 1, 8, 4>(f1, f2, out, g, st);                  // 8 x 8 tile,   72 threads

@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                  "r"(smem_u32(src)), "r"(x), "r"(y), "r"(c), "r"(b)
                  : "memory");
 }
+// shared -> global linear bulk copy (bulk async-group completion); 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_store(void* dst_global, const void* src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_u32(src_shared)),
+                 "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N committed store groups still have to READ their shared-memory source
 template <int N>
