@@ -258,19 +258,18 @@ int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, 
 
 // ------------------------------------------------------------------------------------------------ backward
 constexpr int kBM = 8;     // pixels per thread along x
-constexpr int kCB = 32;    // channels per CTA
 
-// CG channel groups (lanes) x CN channels per thread = kCB; the thread's channels are c = k*CG + cg.
+// CB channels per CTA = CG channel groups (warps) x CN channels per thread; the thread's channels are c = k*CG + cg.
 // TIC = x-displacements handled per register sweep (D must be a multiple of TIC).
-template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED>
+template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
 struct BwdT {
     static constexpr int D = 2 * R + 1;
-    static constexpr int CN = kCB / CG;
+    static constexpr int CN = CB / CG;
     static constexpr int TW = NS * kBM;
     static constexpr int XO = (4 - R % 4) % 4;  // TMA box origins must be 16-byte aligned along x: start XO pixels further left
     static constexpr int P2 = pitch_for(TW + 2 * R + XO + 3);
     static constexpr int R2 = TH + 2 * R;
-    static constexpr int FT = kCB * R2 * P2;      // resident feature tile, floats
+    static constexpr int FT = CB * R2 * P2;      // resident feature tile, floats
     // TMA needs a 16-byte aligned box origin along x, so each shifted plane of the second gradient is staged as a box
     // whose origin is rounded down to a multiple of 4 pixels (4 extra columns) and the residual 0..3 pixel shift is
     // applied when the registers are filled.
@@ -279,9 +278,12 @@ struct BwdT {
     static constexpr int GP = TH * GW;            // one plane tile, floats
     static constexpr int GS = D * GP;             // one gradient stage (D planes), floats
     static constexpr int THREADS = TH * NS * CG;
-    static constexpr size_t SMEM = sizeof(float) * (FT + 2 * GS) + 8 * 3 + 1024;
-    static_assert((FT * 4) % 128 == 0 && (GP * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
-    static_assert(D % TIC == 0 && TH % 8 == 0 && kCB % CG == 0, "bad tile");
+    static constexpr int FH = R2 / 2;             // the feature tile arrives as two boxes of FH rows, each with its own barrier
+    static constexpr size_t SMEM = sizeof(float) * (FT + NSTG * GS) + 8 * (NSTG + 2) + 1024;
+    static_assert((FT * 4) % 128 == 0 && (GP * 4) % 128 == 0 && (CB * FH * P2 * 4) % 128 == 0,
+                  "TMA destinations must stay 128-byte aligned");
+    static_assert(D % TIC == 0 && TH % 8 == 0 && CB % CG == 0 && R2 % 2 == 0 && NSTG >= 2 && NSTG <= D, "bad tile");
+    static_assert(TH <= FH, "the first displacement row must only need the upper half of the feature tile");
     static_assert(SMEM <= 227 * 1024, "tile does not fit in shared memory");
 };
 
@@ -321,7 +323,7 @@ __device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const fl
         float bv[BL];
 #pragma unroll
         for (int i = 0; i < BL; i += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(fp + k * CG * T::R2 * T::P2 + B0 + i);
+            const float4 v = *reinterpret_cast<const float4*>(fp + k * CG * T::FH * T::P2 + B0 + i);
             bv[i] = v.x, bv[i + 1] = v.y, bv[i + 2] = v.z, bv[i + 3] = v.w;
         }
 #pragma unroll
@@ -339,59 +341,69 @@ struct SweepAll {
     }
 };
 
-template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED>
-__global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED>::THREADS, 1)
+template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
+__global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>::THREADS, 1)
     corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapG,
                         float* __restrict__ gI, CorrGeom g, int tiles_x, int tiles_y, int cblocks) {
-    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED>;
+    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
     constexpr int D = T::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* Fs = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
     float* Gs = Fs + T::FT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Gs + 2 * T::GS);  // [0],[1]: gradient stages, [2]: feature tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Gs + NSTG * T::GS);  // [0, NSTG): gradient stages, then the two feature halves
+    uint64_t* fbar = bars + NSTG;
 
-    int bid = blockIdx.x;
-    const int txi = bid % tiles_x;
-    bid /= tiles_x;
-    const int tyi = bid % tiles_y;
-    bid /= tiles_y;
-    const int cbi = bid % cblocks;
-    const int b = bid / cblocks;
-    const int x0 = txi * T::TW, y0 = tyi * TH, c0 = cbi * kCB;
+    auto decode = [&](int bid, int& x0, int& y0, int& c0, int& b) {
+        // channel blocks fastest: the CTAs that stream the same gradient planes run together (L2 hits)
+        const int cbi = bid % cblocks;
+        bid /= cblocks;
+        const int txi = bid % tiles_x;
+        bid /= tiles_x;
+        const int tyi = bid % tiles_y;
+        b = bid / tiles_y;
+        x0 = txi * T::TW, y0 = tyi * TH, c0 = cbi * CB;
+    };
+    int x0, y0, c0, b;
+    decode(blockIdx.x, x0, y0, c0, b);
 
-    // lanes: rows (fastest) x channel groups of ONE strip -> a quarter-warp reads 8 different rows of the feature /
-    // gradient tiles, whose pitches are 4*odd (mod 32): conflict-free 128-bit LDS
+    // lanes: rows (fastest) x strips of ONE channel group; warps: channel groups.  A quarter-warp reads 8 different rows
+    // of the feature / gradient tiles, whose pitches are 4*odd (mod 32): conflict-free 128-bit LDS; and the 32-byte
+    // pieces a warp stores for one channel are the whole rows of the tile (full sectors, 8 lines per store).
     const int tid = threadIdx.x;
     const int row = tid % TH;
-    const int cg = (tid / TH) % CG;
-    const int s = tid / (TH * CG);
+    const int s = (tid / TH) % NS;
+    const int cg = tid / (TH * NS);
 
+    // one displacement row (D planes) of the gradient into stage st, or -- prefetch -- only into the L2
     auto issue_g = [&](int tji, int st) {
         float* dst = Gs + st * T::GS;
         ofr::mbar_expect_tx(&bars[st], T::GS * 4);
 #pragma unroll 1
         for (int tii = 0; tii < D; ++tii) {
-            if (SHIFTED)  // plane of displacement -t, rows shifted by tj here, columns shifted by ti at register fill
-                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0 - R - T::XO + ((tii + T::XO) & ~3), y0 + tji - R,
-                                 (2 * R - tji) * D + (2 * R - tii), b);
-            else
-                ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], x0, y0, tji * D + tii, b);
+            // SHIFTED: plane of displacement -t, rows shifted by tj here, columns shifted by ti at register fill
+            const int cx = SHIFTED ? x0 - R - T::XO + ((tii + T::XO) & ~3) : x0;
+            const int cy = SHIFTED ? y0 + tji - R : y0;
+            const int pl = SHIFTED ? (2 * R - tji) * D + (2 * R - tii) : tji * D + tii;
+            ofr::tma_load_4d(dst + tii * T::GP, &mapG, &bars[st], cx, cy, pl, b);
         }
     };
     if (tid == 0) {
         ofr::tma_prefetch_desc(&mapF);
         ofr::tma_prefetch_desc(&mapG);
-        ofr::mbar_init(&bars[0], 1);
-        ofr::mbar_init(&bars[1], 1);
-        ofr::mbar_init(&bars[2], 1);
+        for (int i = 0; i < NSTG + 2; ++i) ofr::mbar_init(&bars[i], 1);
         ofr::mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
-        ofr::mbar_expect_tx(&bars[2], T::FT * 4);
-        ofr::tma_load_4d(Fs, &mapF, &bars[2], x0 - R - T::XO, y0 - R, c0, b);
+        // feature tile in two halves: the first displacement row only needs the upper one
+        ofr::mbar_expect_tx(&fbar[0], CB * T::FH * T::P2 * 4);
+        ofr::tma_load_4d(Fs, &mapF, &fbar[0], x0 - R - T::XO, y0 - R, c0, b);
         issue_g(0, 0);
-        issue_g(1, 1);
+        ofr::mbar_expect_tx(&fbar[1], CB * T::FH * T::P2 * 4);
+        ofr::tma_load_4d(Fs + CB * T::FH * T::P2, &mapF, &fbar[1], x0 - R - T::XO, y0 - R + T::FH, c0, b);
+        for (int i = 1; i < NSTG; ++i) issue_g(i, i);
+        // (Pulling later displacement rows / the next CTA's tiles into the L2 with cp.async.bulk.prefetch made the
+        // kernel 10-20 % slower: the prefetches queue in the same TMA unit in front of the loads that matter.)
     }
 
     float acc[kBM][T::CN];
@@ -400,17 +412,22 @@ __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED>::THREADS, 1)
 #pragma unroll
         for (int k = 0; k < T::CN; ++k) acc[i][k] = 0.f;
 
-    ofr::mbar_wait(&bars[2], 0);
+    ofr::mbar_wait(&fbar[0], 0);
     for (int tji = 0; tji < D; ++tji) {
-        const int st = tji & 1;
-        ofr::mbar_wait(&bars[st], (tji >> 1) & 1);
+        const int st = tji % NSTG;
+        if (tji == 1) ofr::mbar_wait(&fbar[1], 0);  // rows row + tji, tji >= 1, reach into the lower half
+        ofr::mbar_wait(&bars[st], (tji / NSTG) & 1);
         const float* gp = Gs + st * T::GS + row * T::GW + s * kBM;
-        const float* fp = Fs + (long long)cg * T::R2 * T::P2 + (row + tji) * T::P2 + s * kBM;
+        // feature tile layout: [half][channel][FH rows][P2] (two TMA boxes)
+        const int rr = row + tji, half = rr >= T::FH ? 1 : 0;
+        const float* fp = Fs + half * (CB * T::FH * T::P2) + cg * (T::FH * T::P2) + (rr - half * T::FH) * T::P2 + s * kBM;
         SweepAll<T, R, CG, TIC, SHIFTED, 0>::run(gp, fp, acc);
-        __syncthreads();
-        if (tid == 0 && tji + 2 < D) {
-            ofr::fence_proxy_async();
-            issue_g(tji + 2, st);
+        if (tji + NSTG < D) {
+            __syncthreads();  // every thread is done reading stage st
+            if (tid == 0) {
+                ofr::fence_proxy_async();
+                issue_g(tji + NSTG, st);
+            }
         }
     }
 
@@ -423,8 +440,8 @@ __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED>::THREADS, 1)
             if (c >= g.C) continue;
             float* o = gI + ((long long)b * g.C + c) * hw + (long long)y * g.W;
             if (xb + kBM <= g.W) {
-                *reinterpret_cast<float4*>(o + xb) = make_float4(acc[0][k] * g.scale, acc[1][k] * g.scale, acc[2][k] * g.scale, acc[3][k] * g.scale);
-                *reinterpret_cast<float4*>(o + xb + 4) = make_float4(acc[4][k] * g.scale, acc[5][k] * g.scale, acc[6][k] * g.scale, acc[7][k] * g.scale);
+                __stcs(reinterpret_cast<float4*>(o + xb), make_float4(acc[0][k] * g.scale, acc[1][k] * g.scale, acc[2][k] * g.scale, acc[3][k] * g.scale));
+                __stcs(reinterpret_cast<float4*>(o + xb + 4), make_float4(acc[4][k] * g.scale, acc[5][k] * g.scale, acc[6][k] * g.scale, acc[7][k] * g.scale));
             } else {
 #pragma unroll
                 for (int i = 0; i < kBM; ++i)
@@ -434,16 +451,16 @@ __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED>::THREADS, 1)
     }
 }
 
-template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED>
+template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
 int launch_bwd(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
-    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED>;
+    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
     CUtensorMap mF, mG;
-    if (!ofr::make_tmap_nchw(&mF, feat, g.B, g.C, g.H, g.W, T::P2, T::R2, kCB)) return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mF, feat, g.B, g.C, g.H, g.W, T::P2, T::FH, CB)) return OFR_ENOTSUP;
     if (!ofr::make_tmap_nchw(&mG, gO, g.B, T::D * T::D, g.Hout, g.Wout, T::GW, TH, 1)) return OFR_ENOTSUP;
-    auto kern = corr_bwd_tma_kernel<R, TH, NS, CG, TIC, SHIFTED>;
+    auto kern = corr_bwd_tma_kernel<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
     OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
     const int tiles_x = (g.W + T::TW - 1) / T::TW, tiles_y = (g.H + TH - 1) / TH;
-    const int cblocks = (g.C + kCB - 1) / kCB;
+    const int cblocks = (g.C + CB - 1) / CB;
     const long long nblk = (long long)tiles_x * tiles_y * cblocks * g.B;
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     kern<<<(unsigned)nblk, T::THREADS, T::SMEM, st>>>(mF, mG, gI, g, tiles_x, tiles_y, cblocks);
@@ -455,9 +472,12 @@ template <bool SHIFTED>
 int dispatch_bwd4(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
     // 8 x 32 tiles: 112 KB of shared memory per CTA -> two CTAs per SM, so one CTA's feature-tile load and epilogue
     // overlap the other's arithmetic
-    if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, SHIFTED>(feat, gO, gI, g, st);
-    if (g.W > 8) return launch_bwd<4, 8, 2, 4, 9, SHIFTED>(feat, gO, gI, g, st);
-    return launch_bwd<4, 8, 1, 4, 9, SHIFTED>(feat, gO, gI, g, st);
+    // (16 x 32 tiles with 16 channels per CTA -- same shared memory, half the halo, twice the arithmetic per stage --
+    // measured 8 % slower; a 3-deep ring at one CTA per SM 30 % slower.)
+    if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, SHIFTED, 2, 32>(feat, gO, gI, g, st);
+    // small maps: the whole gradient tile (all 9 displacement rows) is in flight at once -- latency, not bandwidth
+    if (g.W > 8) return launch_bwd<4, 8, 2, 4, 9, SHIFTED, 9, 32>(feat, gO, gI, g, st);
+    return launch_bwd<4, 8, 1, 4, 9, SHIFTED, 9, 32>(feat, gO, gI, g, st);
 }
 
 bool applicable(const CorrGeom& g, int R, const void* a, const void* b, const void* c) {
@@ -473,12 +493,8 @@ int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g
     if (applicable(g, 4, f1, f2, out)) {
         // 7 rows: 7 warps own tj = 0..7 and one warp owns tj = 8 -> 8 warps; a 9-warp CTA would be allocated registers
         // for 12 warps and could not keep the 144 accumulators of the 16-pixel strip
-        if (g.W > 32) {
-            static const int v = getenv("OFR_FWD_V") ? atoi(getenv("OFR_FWD_V")) : 0;  // tuning switch (development only)
-            if (v == 2) return launch_fwd<4, 16, 8, 2, 8, 2>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads, 2 CTAs/SM
-            if (v == 3) return launch_fwd<4, 8, 8, 4, 8, 3>(f1, f2, out, g, st);    // 8 x 32 tile, 8-px strips, 288 threads
-            return launch_fwd<4, 16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
-        }
+        // (8 x 32 tiles at two CTAs per SM and 8-pixel strips with 288 threads both measured slower.)
+        if (g.W > 32) return launch_fwd<4, 16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
         if (g.W > 16) return launch_fwd<4, 16, 8, 2, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads
         if (g.W > 8) return launch_fwd<4, 16, 8, 1, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile,  72 threads
         return launch_fwd<4, 8, 8, 1, 8, 4>(f1, f2, out, g, st);                  // 8 x 8 tile,   72 threads
@@ -500,8 +516,8 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
     if (applicable(g, 10, f1, f2, gO)) {
         // R = 10 (class images of FlowNetC, 16 x 16 or 32 x 32): 8 x 16 tiles, 8 channel groups x 4 channels, 7
         // x-displacements per register sweep
-        if (gI1) rc = launch_bwd<10, 8, 2, 8, 7, false>(f2, gO, gI1, g, st);
-        if (rc == OFR_OK && gI2) rc = launch_bwd<10, 8, 2, 8, 7, true>(f1, gO, gI2, g, st);
+        if (gI1) rc = launch_bwd<10, 8, 2, 8, 7, false, 2, 32>(f2, gO, gI1, g, st);
+        if (rc == OFR_OK && gI2) rc = launch_bwd<10, 8, 2, 8, 7, true, 2, 32>(f1, gO, gI2, g, st);
         return rc;
     }
     return OFR_ENOTSUP;

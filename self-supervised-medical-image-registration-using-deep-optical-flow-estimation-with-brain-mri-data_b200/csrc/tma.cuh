@@ -76,6 +76,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(b)
         : "memory");
 }
+// pull a box into the L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int x, int y, int c, int b) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(x), "r"(y),
+                 "r"(c), "r"(b)
+                 : "memory");
+}
 // shared -> global tensor store (bulk async-group completion); out-of-range box elements are not written
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int x, int y, int c, int b) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
