@@ -31,6 +31,7 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "PWC-Net train slice-pairs/s @1/2/4/8 B200; corr+warp kernel % of roofline"
 UNIT = "slice-pairs/s"
+FMA_PEAK_TFLOPS = 72.3  # measured: profiles/r01_fma_peak.txt
 
 
 def peaks():
@@ -238,6 +239,9 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": round(dom["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
                     "avg_launch_us": dom["avg_us"], "tflops_fp32": dom["tflops"],
+                    "fp32_fma_peak_tflops": FMA_PEAK_TFLOPS, "fp32_fma_frac": round(dom["tflops"] / FMA_PEAK_TFLOPS, 4),
+                    "fp32_fma_peak_source": "measured on this pool's B200 with tools/micro/fma_peak.cu (d = a*b + d, "
+                                            "register operands; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.5)",
                     "hot_path_ms_per_step": round(ours_ms, 3), "hot_path_share_of_step": round(ours_ms / ms_per_step, 4)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
