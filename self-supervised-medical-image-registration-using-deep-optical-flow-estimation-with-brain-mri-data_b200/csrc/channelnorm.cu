@@ -3,17 +3,13 @@
 //   fwd: out[b,0,p] = sqrt(sum_c x[b,c,p]^2)            algorithmic bytes 4*B*HW*(C+1)
 //   bwd: gI[b,c,p]  = gO[b,0,p] * x[b,c,p] / (out[b,0,p] + 1e-8)        4*B*HW*(2C+2)
 //
-// Pure HBM streaming.  Each thread owns VEC consecutive pixels (128-bit loads and
-// stores when HW % 4 == 0 and the bases are 16-byte aligned), loops the channels,
-// and the grid is a whole number of waves over the 148 SMs (grid-stride).
+// Pure HBM streaming.  Each thread owns kVPT vectors of VEC consecutive pixels (128-bit loads and
+// stores when HW % 4 == 0 and the bases are 16-byte aligned) and loops the channels.
 #include "ofr_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kCtasPerSm = 8;
-// every launch covers the whole tensor with one vector per thread (no grid-stride tail): the block scheduler keeps
-// 8 x 256 threads resident per SM, each with its loads in flight
 
 template <int VEC>
 struct Pix;
@@ -22,43 +18,66 @@ struct Pix<4> {
     using T = float4;
     static __device__ __forceinline__ T ld(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
     static __device__ __forceinline__ void st(float* p, T v) { __stcs(reinterpret_cast<float4*>(p), v); }
+    static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ T fma(T a, T b, T c) {
+        return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+    }
+    static __device__ __forceinline__ T sqrt(T a) { return make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w)); }
+    static __device__ __forceinline__ T mul(T a, T b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+    static __device__ __forceinline__ T ratio(T g, T o) {
+        return make_float4(g.x / (o.x + 1e-8f), g.y / (o.y + 1e-8f), g.z / (o.z + 1e-8f), g.w / (o.w + 1e-8f));
+    }
 };
 template <>
 struct Pix<1> {
     using T = float;
     static __device__ __forceinline__ T ld(const float* p) { return __ldcs(p); }
     static __device__ __forceinline__ void st(float* p, T v) { __stcs(p, v); }
+    static __device__ __forceinline__ T zero() { return 0.f; }
+    static __device__ __forceinline__ T fma(T a, T b, T c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ T sqrt(T a) { return sqrtf(a); }
+    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    static __device__ __forceinline__ T ratio(T g, T o) { return g / (o + 1e-8f); }
 };
 
+constexpr int kVPT = 4;  // vectors per thread: their loads are all issued before the first use (bytes in flight per SM
+                         // = resident threads x kVPT x 16 B; one vector per thread left the HBM pipe half empty)
+
+// thread -> vectors (blockIdx.x * kVPT + j) * kThreads + threadIdx.x, j < kVPT: every load / store of a warp is one
+// contiguous 512-byte run
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                               int C, long long hw, long long total_vec) {
     const long long hwv = hw / VEC;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / hwv, p = (i - b * hwv) * VEC;
-        const float* xp = x + b * C * hw + p;
-        if constexpr (VEC == 4) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int c = 0; c < C; ++c) {
-                float4 v = Pix<4>::ld(xp + (long long)c * hw);
-                s.x = fmaf(v.x, v.x, s.x);
-                s.y = fmaf(v.y, v.y, s.y);
-                s.z = fmaf(v.z, v.z, s.z);
-                s.w = fmaf(v.w, v.w, s.w);
-            }
-            Pix<4>::st(out + b * hw + p, make_float4(sqrtf(s.x), sqrtf(s.y), sqrtf(s.z), sqrtf(s.w)));
-        } else {
-            float s = 0.f;
-#pragma unroll 4
-            for (int c = 0; c < C; ++c) {
-                float v = Pix<1>::ld(xp + (long long)c * hw);
-                s = fmaf(v, v, s);
-            }
-            Pix<1>::st(out + b * hw + p, sqrtf(s));
+    const long long i0 = (long long)blockIdx.x * kVPT * kThreads + threadIdx.x;
+    const float* xp[kVPT];
+    float* op[kVPT];
+    bool ok[kVPT];
+#pragma unroll
+    for (int j = 0; j < kVPT; ++j) {
+        const long long i = i0 + (long long)j * kThreads;
+        ok[j] = i < total_vec;
+        const long long ic = ok[j] ? i : 0;
+        const long long b = ic / hwv, p = (ic - b * hwv) * VEC;
+        xp[j] = x + b * C * hw + p;
+        op[j] = out + b * hw + p;
+    }
+    typename Pix<VEC>::T s[kVPT];
+#pragma unroll
+    for (int j = 0; j < kVPT; ++j) s[j] = Pix<VEC>::zero();
+    for (int c = 0; c < C; ++c) {
+        typename Pix<VEC>::T v[kVPT];
+#pragma unroll
+        for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
+#pragma unroll
+        for (int j = 0; j < kVPT; ++j) {
+            s[j] = Pix<VEC>::fma(v[j], v[j], s[j]);
+            xp[j] += hw;
         }
     }
+#pragma unroll
+    for (int j = 0; j < kVPT; ++j)
+        if (ok[j]) Pix<VEC>::st(op[j], Pix<VEC>::sqrt(s[j]));
 }
 
 template <int VEC>
@@ -66,28 +85,30 @@ __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __res
                                                               const float* __restrict__ gO, float* __restrict__ gI,
                                                               int C, long long hw, long long total_vec) {
     const long long hwv = hw / VEC;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / hwv, p = (i - b * hwv) * VEC;
-        const float* xp = x + b * C * hw + p;
-        float* gp = gI + b * C * hw + p;
-        if constexpr (VEC == 4) {
-            const float4 o = Pix<4>::ld(out + b * hw + p);
-            const float4 g = Pix<4>::ld(gO + b * hw + p);
-            float4 r;  // gO / (out + 1e-8), one division per pixel instead of per element
-            r.x = g.x / (o.x + 1e-8f);
-            r.y = g.y / (o.y + 1e-8f);
-            r.z = g.z / (o.z + 1e-8f);
-            r.w = g.w / (o.w + 1e-8f);
-#pragma unroll 4
-            for (int c = 0; c < C; ++c) {
-                float4 v = Pix<4>::ld(xp + (long long)c * hw);
-                Pix<4>::st(gp + (long long)c * hw, make_float4(v.x * r.x, v.y * r.y, v.z * r.z, v.w * r.w));
-            }
-        } else {
-            const float r = Pix<1>::ld(gO + b * hw + p) / (Pix<1>::ld(out + b * hw + p) + 1e-8f);
-#pragma unroll 4
-            for (int c = 0; c < C; ++c) Pix<1>::st(gp + (long long)c * hw, Pix<1>::ld(xp + (long long)c * hw) * r);
+    const long long i0 = (long long)blockIdx.x * kVPT * kThreads + threadIdx.x;
+    const float* xp[kVPT];
+    float* gp[kVPT];
+    bool ok[kVPT];
+    typename Pix<VEC>::T r[kVPT];  // gO / (out + 1e-8), one division per pixel instead of per element
+#pragma unroll
+    for (int j = 0; j < kVPT; ++j) {
+        const long long i = i0 + (long long)j * kThreads;
+        ok[j] = i < total_vec;
+        const long long ic = ok[j] ? i : 0;
+        const long long b = ic / hwv, p = (ic - b * hwv) * VEC;
+        xp[j] = x + b * C * hw + p;
+        gp[j] = gI + b * C * hw + p;
+        r[j] = Pix<VEC>::ratio(Pix<VEC>::ld(gO + b * hw + p), Pix<VEC>::ld(out + b * hw + p));
+    }
+    for (int c = 0; c < C; ++c) {
+        typename Pix<VEC>::T v[kVPT];
+#pragma unroll
+        for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
+#pragma unroll
+        for (int j = 0; j < kVPT; ++j) {
+            if (ok[j]) Pix<VEC>::st(gp[j], Pix<VEC>::mul(v[j], r[j]));
+            xp[j] += hw;
+            gp[j] += hw;
         }
     }
 }
@@ -100,10 +121,10 @@ extern "C" int ofr_chnorm_fwd(const float* x, float* out, int B, int C, int H, i
     cudaStream_t st = (cudaStream_t)stream;
     if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out)) {
         const long long n = (long long)B * hw / 4;
-        chnorm_fwd_kernel<4><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, C, hw, n);
+        chnorm_fwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_fwd_kernel<1><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, C, hw, n);
+        chnorm_fwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;
@@ -116,10 +137,10 @@ extern "C" int ofr_chnorm_bwd(const float* x, const float* out, const float* gO,
     cudaStream_t st = (cudaStream_t)stream;
     if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && ofr::aligned16(gO) && ofr::aligned16(gI)) {
         const long long n = (long long)B * hw / 4;
-        chnorm_bwd_kernel<4><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
+        chnorm_bwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_bwd_kernel<1><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
+        chnorm_bwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;

@@ -342,9 +342,9 @@ struct SweepAll {
 };
 
 template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
-__global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>::THREADS, 1)
-    corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapG,
-                        float* __restrict__ gI, CorrGeom g, int tiles_x, int tiles_y, int cblocks) {
+__device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const CUtensorMap& mapG,
+                                                  float* __restrict__ gI, const CorrGeom& g, int tiles_x, int tiles_y,
+                                                  int cblocks) {
     using T = BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
     constexpr int D = T::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -451,33 +451,58 @@ __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>::T
     }
 }
 
-template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
-int launch_bwd(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
-    using T = BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
-    CUtensorMap mF, mG;
-    if (!ofr::make_tmap_nchw(&mF, feat, g.B, g.C, g.H, g.W, T::P2, T::FH, CB)) return OFR_ENOTSUP;
-    if (!ofr::make_tmap_nchw(&mG, gO, g.B, T::D * T::D, g.Hout, g.Wout, T::GW, TH, 1)) return OFR_ENOTSUP;
-    auto kern = corr_bwd_tma_kernel<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
-    OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-    const int tiles_x = (g.W + T::TW - 1) / T::TW, tiles_y = (g.H + TH - 1) / TH;
+// Both gradients in ONE launch: blockIdx.y picks the direction (0: gI1 from f2, 1: gI2 from f1).  The two CTAs that
+// stream the same gradient planes run close together (the second read is an L2 hit), and on small maps the fixed
+// launch / first-load latency is paid once instead of twice.  `first` = direction of blockIdx.y == 0 when only one
+// gradient is wanted.
+template <int R, int TH, int NS, int CG, int TIC, int NSTG, int CB>
+__global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, true, NSTG, CB>::THREADS, 1)
+    corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapG0,
+                        const __grid_constant__ CUtensorMap mapF1, const __grid_constant__ CUtensorMap mapG1,
+                        float* __restrict__ gI1, float* __restrict__ gI2, CorrGeom g, int tiles_x, int tiles_y,
+                        int cblocks, int first) {
+    if ((int)blockIdx.y + first == 0)
+        corr_bwd_tma_body<R, TH, NS, CG, TIC, false, NSTG, CB>(mapF2, mapG0, gI1, g, tiles_x, tiles_y, cblocks);
+    else
+        corr_bwd_tma_body<R, TH, NS, CG, TIC, true, NSTG, CB>(mapF1, mapG1, gI2, g, tiles_x, tiles_y, cblocks);
+}
+
+template <int R, int TH, int NS, int CG, int TIC, int NSTG, int CB>
+int launch_bwd(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
+               cudaStream_t st) {
+    using T0 = BwdT<R, TH, NS, CG, TIC, false, NSTG, CB>;
+    using T1 = BwdT<R, TH, NS, CG, TIC, true, NSTG, CB>;
+    CUtensorMap mF2, mG0, mF1, mG1;
+    if (!ofr::make_tmap_nchw(&mF2, f2, g.B, g.C, g.H, g.W, T0::P2, T0::FH, CB)) return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mF1, f1, g.B, g.C, g.H, g.W, T1::P2, T1::FH, CB)) return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mG0, gO, g.B, T0::D * T0::D, g.Hout, g.Wout, T0::GW, TH, 1)) return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mG1, gO, g.B, T1::D * T1::D, g.Hout, g.Wout, T1::GW, TH, 1)) return OFR_ENOTSUP;
+    auto kern = corr_bwd_tma_kernel<R, TH, NS, CG, TIC, NSTG, CB>;
+    constexpr size_t smem = T0::SMEM > T1::SMEM ? T0::SMEM : T1::SMEM;
+    OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x = (g.W + T0::TW - 1) / T0::TW, tiles_y = (g.H + TH - 1) / TH;
     const int cblocks = (g.C + CB - 1) / CB;
     const long long nblk = (long long)tiles_x * tiles_y * cblocks * g.B;
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
-    kern<<<(unsigned)nblk, T::THREADS, T::SMEM, st>>>(mF, mG, gI, g, tiles_x, tiles_y, cblocks);
+    const int ndir = (gI1 ? 1 : 0) + (gI2 ? 1 : 0);
+    if (ndir == 0) return OFR_OK;
+    dim3 grid((unsigned)nblk, (unsigned)ndir);
+    kern<<<grid, T0::THREADS, smem, st>>>(mF2, mG0, mF1, mG1, gI1, gI2, g, tiles_x, tiles_y, cblocks, gI1 ? 0 : 1);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
 
-template <bool SHIFTED>
-int dispatch_bwd4(const float* feat, const float* gO, float* gI, const CorrGeom& g, cudaStream_t st) {
+int dispatch_bwd4(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
+                  cudaStream_t st) {
     // 8 x 32 tiles: 112 KB of shared memory per CTA -> two CTAs per SM, so one CTA's feature-tile load and epilogue
     // overlap the other's arithmetic
     // (16 x 32 tiles with 16 channels per CTA -- same shared memory, half the halo, twice the arithmetic per stage --
     // measured 8 % slower; a 3-deep ring at one CTA per SM 30 % slower.)
-    if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, SHIFTED, 2, 32>(feat, gO, gI, g, st);
-    // small maps: the whole gradient tile (all 9 displacement rows) is in flight at once -- latency, not bandwidth
-    if (g.W > 8) return launch_bwd<4, 8, 2, 4, 9, SHIFTED, 9, 32>(feat, gO, gI, g, st);
-    return launch_bwd<4, 8, 1, 4, 9, SHIFTED, 9, 32>(feat, gO, gI, g, st);
+    if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, 2, 32>(f1, f2, gO, gI1, gI2, g, st);
+    // small maps: the whole gradient tile (all 9 displacement rows) is in flight at once -- latency, not bandwidth --
+    // and there are too few tiles to fill the machine, so the channels are spread over more warps (4 / 2 per thread)
+    if (g.W > 8) return launch_bwd<4, 8, 2, 8, 9, 9, 32>(f1, f2, gO, gI1, gI2, g, st);
+    return launch_bwd<4, 8, 1, 16, 9, 9, 32>(f1, f2, gO, gI1, gI2, g, st);
 }
 
 bool applicable(const CorrGeom& g, int R, const void* a, const void* b, const void* c) {
@@ -507,18 +532,13 @@ int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g
 int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
                  cudaStream_t st) {
     if ((gI1 && !ofr::aligned16(gI1)) || (gI2 && !ofr::aligned16(gI2))) return OFR_ENOTSUP;
-    int rc = OFR_OK;
     if (applicable(g, 4, f1, f2, gO)) {
-        if (gI1) rc = dispatch_bwd4<false>(f2, gO, gI1, g, st);
-        if (rc == OFR_OK && gI2) rc = dispatch_bwd4<true>(f1, gO, gI2, g, st);
-        return rc;
+        return dispatch_bwd4(f1, f2, gO, gI1, gI2, g, st);
     }
     if (applicable(g, 10, f1, f2, gO)) {
         // R = 10 (class images of FlowNetC, 16 x 16 or 32 x 32): 8 x 16 tiles, 8 channel groups x 4 channels, 7
         // x-displacements per register sweep
-        if (gI1) rc = launch_bwd<10, 8, 2, 8, 7, false, 2, 32>(f2, gO, gI1, g, st);
-        if (rc == OFR_OK && gI2) rc = launch_bwd<10, 8, 2, 8, 7, true, 2, 32>(f1, gO, gI2, g, st);
-        return rc;
+        return launch_bwd<10, 8, 2, 8, 7, 2, 32>(f1, f2, gO, gI1, gI2, g, st);
     }
     return OFR_ENOTSUP;
 }
