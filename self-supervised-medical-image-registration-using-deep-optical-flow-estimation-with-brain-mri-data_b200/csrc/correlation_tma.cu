@@ -24,10 +24,14 @@
 //                                                                  its rows shifted by tj; the x shift is applied
 //                                                                  when the registers are filled)
 //   No atomics, fixed summation order -> bitwise reproducible.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "corr_internal.cuh"
 #include "tma.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -236,6 +240,180 @@ __global__ void __maxnreg__(224)
             ++tile_k;
         }
     }
+}
+
+// Small maps (too few tiles to fill the machine: the 8x8 ... 32x32 levels of the PWC pyramid): the channel chunks of ONE
+// tile are split over the KS CTAs of a thread-block cluster.  Each CTA runs the same ring / register tile over its
+// chunk range, parks its partial cost volume in its own shared memory, and after a cluster barrier every CTA adds the
+// KS partials of its share of the output planes through distributed shared memory in rank order (deterministic) and
+// streams them out with whole-line stores.
+template <int R, int M, int TH, int NS, int CK, int NST>
+__global__ void __maxnreg__(224)
+    corr_fwd_split_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                          float* __restrict__ out, CorrGeom g, int tiles_x, int tiles_y, int ks) {
+    using T = FwdT<R, M, TH, NS, CK, NST>;
+    constexpr int D = T::D;
+    constexpr int NOUT = D * D * TH * T::TW;  // floats of one partial cost-volume tile
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw + ((1024u - (ofr::smem_u32(smem_raw) & 1023u)) & 1023u));
+    float* part = smem + T::STAGE * NST;  // [D*D][TH][TW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + NOUT);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+
+    const int tid = threadIdx.x;
+    int tj, s, row;
+    if (T::kNine) {
+        if (tid < T::T1) {
+            tj = tid & 7;
+            const int q = tid >> 3;
+            s = q % NS;
+            row = q / NS;
+        } else {
+            tj = 8;
+            const int q = tid - T::T1;
+            row = q % TH;
+            s = q / TH;
+        }
+    } else {
+        const int q = tid >> 3;
+        const int combo = q % (TH * NS);
+        tj = (q / (TH * NS)) * 8 + (tid & 7);
+        s = combo % NS;
+        row = combo / NS;
+    }
+    const bool active = tj < D;
+    const int tjc = active ? tj : D - 1;
+
+    int t = blockIdx.x / ks;
+    const int x0 = (t % tiles_x) * T::TW;
+    t /= tiles_x;
+    const int y0 = (t % tiles_y) * TH, b = t / tiles_y;
+    const int nchunks = (g.C + CK - 1) / CK, per = (nchunks + ks - 1) / ks;
+    const int cbeg = min(rank * per, nchunks), total = min(cbeg + per, nchunks) - cbeg;  // this rank's chunks
+
+    auto issue = [&](int q) {
+        const int c0 = (cbeg + q) * CK, st = q % NST;
+        float* dst = smem + st * T::STAGE;
+        ofr::mbar_expect_tx(&bars[st], T::STAGE * 4);
+        ofr::tma_load_4d(dst, &map1, &bars[st], x0, y0, c0, b);
+        ofr::tma_load_4d(dst + T::F1, &map2, &bars[st], x0 - R - T::XO, y0 - R, c0, b);
+    };
+    if (tid == 0) {
+        ofr::tma_prefetch_desc(&map1);
+        ofr::tma_prefetch_desc(&map2);
+        for (int i = 0; i < NST; ++i) ofr::mbar_init(&bars[i], 1);
+        ofr::mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < NST && i < total; ++i) issue(i);
+
+    float acc[M][D];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[i][j] = 0.f;
+
+    for (int q = 0; q < total; ++q) {
+        const int st = q % NST;
+        ofr::mbar_wait(&bars[st], (q / NST) & 1);
+        const float* ap = smem + st * T::STAGE + row * T::P1 + s * M;
+        const float* bp = smem + st * T::STAGE + T::F1 + (row + tjc) * T::P2 + s * M;
+#pragma unroll 1
+        for (int cc = 0; cc < CK; ++cc) {
+            float a[M], bv[T::BL];
+#pragma unroll
+            for (int i = 0; i < M; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(ap + cc * TH * T::P1 + i);
+                a[i] = v.x, a[i + 1] = v.y, a[i + 2] = v.z, a[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < T::BL; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(bp + cc * T::R2 * T::P2 + i);
+                bv[i] = v.x, bv[i + 1] = v.y, bv[i + 2] = v.z, bv[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) acc[i][j] = fmaf(a[i], bv[i + j + T::XO], acc[i][j]);
+        }
+        if (q + NST < total) {
+            __syncthreads();  // every thread is done reading stage st
+            if (tid == 0) {
+                ofr::fence_proxy_async();
+                issue(q + NST);
+            }
+        }
+    }
+    // partial tile -> own shared memory (plane-major, dense rows)
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            float* dst = part + (tj * D + j) * (TH * T::TW) + row * T::TW + s * M;
+#pragma unroll
+            for (int i = 0; i < M; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i][j], acc[i + 1][j], acc[i + 2][j], acc[i + 3][j]);
+        }
+    }
+    cluster.sync();
+    // every CTA reduces the 16-byte chunks v = rank*THREADS + tid (mod ks*THREADS) of the tile over all ranks, in order
+    const size_t hw = (size_t)g.Hout * g.Wout;
+    constexpr int TW4 = T::TW / 4;
+    for (int v = rank * T::THREADS + tid; v < NOUT / 4; v += ks * T::THREADS) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < ks; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(cluster.map_shared_rank(part, r) + 4 * v);
+            sum.x += x.x, sum.y += x.y, sum.z += x.z, sum.w += x.w;
+        }
+        const int plane = v / (TH * TW4), rem = v - plane * (TH * TW4);
+        const int ry = rem / TW4, cx = (rem - ry * TW4) * 4;
+        const int y = y0 + ry, x = x0 + cx;
+        if (y < g.Hout && x < g.Wout)
+            __stcs(reinterpret_cast<float4*>(out + ((size_t)b * D * D + plane) * hw + (size_t)y * g.Wout + x),
+                   make_float4(sum.x * g.scale, sum.y * g.scale, sum.z * g.scale, sum.w * g.scale));
+    }
+    cluster.sync();  // remote shared memory must outlive the reads
+}
+
+template <int R, int M, int TH, int NS, int CK, int NST>
+int launch_fwd_split(const float* f1, const float* f2, float* out, const CorrGeom& g, int ks, cudaStream_t st) {
+    using T = FwdT<R, M, TH, NS, CK, NST>;
+    CUtensorMap m1, m2;
+    if (!ofr::make_tmap_nchw(&m1, f1, g.B, g.C, g.H, g.W, T::P1, TH, CK)) return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&m2, f2, g.B, g.C, g.H, g.W, T::P2, T::R2, CK)) return OFR_ENOTSUP;
+    auto kern = corr_fwd_split_kernel<R, M, TH, NS, CK, NST>;
+    constexpr size_t smem = sizeof(float) * (T::STAGE * NST + T::D * T::D * TH * T::TW) + 8 * NST + 1024;
+    static_assert(smem <= 227 * 1024, "split tile does not fit in shared memory");
+    OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x = (g.Wout + T::TW - 1) / T::TW, tiles_y = (g.Hout + TH - 1) / TH;
+    const long long ntiles = (long long)tiles_x * tiles_y * g.B;
+    if (ntiles * ks >= (1ll << 31)) return OFR_ENOTSUP;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ntiles * ks));
+    cfg.blockDim = dim3(T::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OFR_CUDA(cudaLaunchKernelEx(&cfg, kern, m1, m2, out, g, tiles_x, tiles_y, ks));
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+// channel split for a geometry with `ntiles` tiles and `nchunks` channel chunks: 1 (no split), 2, 4 or 8
+int split_for(long long ntiles, int nchunks) {
+    // measured on the PWC pyramid (B = 24): 8x8 maps 23.7 -> 10.0 us at ks = 4, 16x16 maps 23.4 -> 18.9 us at ks = 2,
+    // 32x32 maps get slower with any split (the 83 KB partial tile dominates) -> split only while the grid stays
+    // within about two thirds of the SMs
+    int ks = 1;
+    while (ks < 8 && ks * 2 <= nchunks && ntiles * ks * 2 * 10 <= 7ll * ofr::sm_count()) ks *= 2;
+    return ks;
 }
 
 template <int R, int M, int TH, int NS, int CK, int NST>
@@ -520,9 +698,21 @@ int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g
         // for 12 warps and could not keep the 144 accumulators of the 16-pixel strip
         // (8 x 32 tiles at two CTAs per SM and 8-pixel strips with 288 threads both measured slower.)
         if (g.W > 32) return launch_fwd<4, 16, 7, 4, 8, 3>(f1, f2, out, g, st);   // 7 x 64 tile, 252 threads
-        if (g.W > 16) return launch_fwd<4, 16, 8, 2, 8, 3>(f1, f2, out, g, st);   // 8 x 32 tile, 144 threads
-        if (g.W > 8) return launch_fwd<4, 16, 8, 1, 8, 4>(f1, f2, out, g, st);    // 8 x 16 tile,  72 threads
-        return launch_fwd<4, 8, 8, 1, 8, 4>(f1, f2, out, g, st);                  // 8 x 8 tile,   72 threads
+        const int nchunks = (g.C + 7) / 8;
+        const long long tiles_y8 = (g.Hout + 7) / 8;
+        if (g.W > 16) {  // 8 x 32 tile, 144 threads
+            const int ks = split_for(tiles_y8 * g.B, nchunks);
+            if (ks > 1) return launch_fwd_split<4, 16, 8, 2, 8, 3>(f1, f2, out, g, ks, st);
+            return launch_fwd<4, 16, 8, 2, 8, 3>(f1, f2, out, g, st);
+        }
+        if (g.W > 8) {   // 8 x 16 tile, 72 threads
+            const int ks = split_for(tiles_y8 * g.B, nchunks);
+            if (ks > 1) return launch_fwd_split<4, 16, 8, 1, 8, 4>(f1, f2, out, g, ks, st);
+            return launch_fwd<4, 16, 8, 1, 8, 4>(f1, f2, out, g, st);
+        }
+        const int ks = split_for(tiles_y8 * g.B, nchunks);  // 8 x 8 tile, 72 threads
+        if (ks > 1) return launch_fwd_split<4, 8, 8, 1, 8, 4>(f1, f2, out, g, ks, st);
+        return launch_fwd<4, 8, 8, 1, 8, 4>(f1, f2, out, g, st);
     }
     if (applicable(g, 10, f1, f2, out))
         return launch_fwd<10, 8, 4, 2, 8, 3>(f1, f2, out, g, st);                 // 4 x 16 tile, 192 threads (3 x 8 tj lanes)

@@ -26,7 +26,6 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxCtasPerScale = 1184;  // eight CTAs per SM on the 148 SMs
 constexpr int kHardMaxCtasPerScale = 8192;  // batches beyond this many images per scale are refused
 constexpr int kNumPart = 11;           // partial slots per CTA, see enum
 
@@ -513,7 +512,7 @@ size_t ws_bytes_for(int total_ctas) { return ofr::align_up(sizeof(double) * kNum
 extern "C" size_t ofr_loss_workspace(int n_scales) {
     if (n_scales < 1 || n_scales > OFR_LOSS_MAX_SCALES) return 0;
     // upper bound that does not depend on the batch: fill_params never uses more than kHardMaxCtasPerScale CTAs
-    // per scale (and more than kMaxCtasPerScale only for batches beyond 1184 images).
+    // per scale.
     return ws_bytes_for(kHardMaxCtasPerScale * n_scales);
 }
 
