@@ -76,6 +76,14 @@ int ofr_corr_fwd(const float* f1, const float* f2, float* out,
                  int B, int C, int H, int W,
                  int pad, int k, int md, int s1, int s2,
                  void* ws, size_t ws_bytes, ofr_stream_t stream);
+/* Same with LeakyReLU(negative_slope) fused into the store of the cost volume -- the activation that follows every
+ * correlation of the reference (PWC/models/PWCNet.py:201,216,230,244,260; flownet2/networks/FlowNetC.py:89;
+ * FlowNetS/util.py:72).  negative_slope = 1 is ofr_corr_fwd.  The backward of the activation is the caller's
+ * (mask the upstream gradient with the sign of the output, then ofr_corr_bwd). */
+int ofr_corr_fwd_act(const float* f1, const float* f2, float* out,
+                     int B, int C, int H, int W,
+                     int pad, int k, int md, int s1, int s2, float negative_slope,
+                     void* ws, size_t ws_bytes, ofr_stream_t stream);
 /* gI1 / gI2 may each be NULL to skip that gradient. */
 int ofr_corr_bwd(const float* f1, const float* f2, const float* gO,
                  float* gI1, float* gI2,
@@ -104,6 +112,11 @@ enum {
 int ofr_resample_fwd(const float* in1, const float* flow, float* out,
                      int B, int C, int Hin, int Win, int Hf, int Wf,
                      int mode, ofr_stream_t stream);
+/* Same with the flow multiplied by flow_scale first (float32 product, as `flo * 0.625` etc. at the PWC-Net call
+ * sites PWC/models/PWCNet.py:214,228,242,258). */
+int ofr_resample_fwd_scaled(const float* in1, const float* flow, float* out,
+                            int B, int C, int Hin, int Win, int Hf, int Wf, int mode, float flow_scale,
+                            ofr_stream_t stream);
 /* Bytes of scratch ofr_resample_bwd needs when gI1 != NULL (0 when only gI2 is wanted). */
 size_t ofr_resample_bwd_workspace(int B, int C, int Hin, int Win, int Hf, int Wf, int mode);
 /* Deterministic backward.  gI1 [B,C,Hin,Win] and/or gI2 [B,2,Hf,Wf]; either may be NULL.
@@ -113,6 +126,11 @@ size_t ofr_resample_bwd_workspace(int B, int C, int Hin, int Win, int Hf, int Wf
 int ofr_resample_bwd(const float* in1, const float* flow, const float* gO,
                      float* gI1, float* gI2,
                      int B, int C, int Hin, int Win, int Hf, int Wf, int mode,
+                     void* ws, size_t ws_bytes, ofr_stream_t stream);
+/* Backward of ofr_resample_fwd_scaled: gI2 is the gradient of the UNSCALED flow. */
+int ofr_resample_bwd_scaled(const float* in1, const float* flow, const float* gO,
+                     float* gI1, float* gI2,
+                     int B, int C, int Hin, int Win, int Hf, int Wf, int mode, float flow_scale,
                      void* ws, size_t ws_bytes, ofr_stream_t stream);
 
 /* ------------------------------------------------------------------ ChannelNorm

@@ -74,8 +74,11 @@ def _declare(lib):
         "ofr_corr_out_shape": (c_int, [c_int] * 7 + [ip, ip, ip]),
         "ofr_corr_workspace": (c_size_t, [c_int] * 10),
         "ofr_corr_fwd": (c_int, [vp, vp, vp] + [c_int] * 9 + [vp, c_size_t, vp]),
+        "ofr_corr_fwd_act": (c_int, [vp, vp, vp] + [c_int] * 9 + [ctypes.c_float, vp, c_size_t, vp]),
         "ofr_corr_bwd": (c_int, [vp, vp, vp, vp, vp] + [c_int] * 9 + [vp, c_size_t, vp]),
         "ofr_resample_fwd": (c_int, [vp, vp, vp] + [c_int] * 7 + [vp]),
+        "ofr_resample_fwd_scaled": (c_int, [vp, vp, vp] + [c_int] * 7 + [ctypes.c_float, vp]),
+        "ofr_resample_bwd_scaled": (c_int, [vp, vp, vp, vp, vp] + [c_int] * 7 + [ctypes.c_float, vp, c_size_t, vp]),
         "ofr_resample_bwd_workspace": (c_size_t, [c_int] * 7),
         "ofr_resample_bwd": (c_int, [vp, vp, vp, vp, vp] + [c_int] * 7 + [vp, c_size_t, vp]),
         "ofr_chnorm_fwd": (c_int, [vp, vp] + [c_int] * 4 + [vp]),
@@ -94,8 +97,9 @@ def _declare(lib):
 
 
 EXPORTS = ["ofr_abi_version", "ofr_error_string", "ofr_launch_count", "ofr_corr_out_shape", "ofr_corr_workspace",
-           "ofr_corr_fwd",
-           "ofr_corr_bwd", "ofr_resample_fwd", "ofr_resample_bwd_workspace", "ofr_resample_bwd",
+           "ofr_corr_fwd", "ofr_corr_fwd_act",
+           "ofr_corr_bwd", "ofr_resample_fwd", "ofr_resample_fwd_scaled", "ofr_resample_bwd_workspace", "ofr_resample_bwd",
+           "ofr_resample_bwd_scaled",
            "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd"]
 
 

@@ -9,7 +9,14 @@ struct CorrGeom {
     int pad, k, md, s1, s2;
     int r, D, Hout, Wout;
     float scale;  // 1 / (k*k*C)
+    float slope;  // fused LeakyReLU on the forward output (PWCNet.py:201, FlowNetC.py:89); 1 = none
 };
+
+// output element: scaled sum, then the optional LeakyReLU
+__device__ __forceinline__ float corr_out(float acc, const CorrGeom& g) {
+    const float v = acc * g.scale;
+    return v > 0.f ? v : v * g.slope;
+}
 
 // TMA-staged kernels for Correlation(4,1,4,1,1).  Return OFR_ENOTSUP (nothing launched) when the geometry or the
 // pointer alignment does not fit; the caller then falls back to the generic kernels.

@@ -32,6 +32,7 @@ bool make_geom(CorrGeom& g, int B, int C, int H, int W, int pad, int k, int md, 
     g.Hout = (ph + s1 - 1) / s1;
     g.Wout = (pw + s1 - 1) / s1;
     g.scale = 1.0f / (float)(k * k * C);
+    g.slope = 1.0f;
     return true;
 }
 
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) corr_fwd_generic_kernel(const float* __re
                 for (int w = 0; w < g.k; ++w)
                     acc = fmaf(rd(a, y1 + h, x1 + w, g.H, g.W), rd(bb, y2 + h, x2 + w, g.H, g.W), acc);
         }
-        out[i] = acc * g.scale;
+        out[i] = ofr::corr_out(acc, g);
     }
 }
 
@@ -280,13 +281,13 @@ __global__ void __launch_bounds__(Cfg::THREADS)
             if (S2 == 1 && xb + M <= g.Wout) {
 #pragma unroll
                 for (int i = 0; i < M; i += 4)
-                    ofr::stcs4(o + xb + i, make_float4(acc[i][j] * g.scale, acc[i + 1][j] * g.scale,
-                                                       acc[i + 2][j] * g.scale, acc[i + 3][j] * g.scale));
+                    ofr::stcs4(o + xb + i, make_float4(ofr::corr_out(acc[i][j], g), ofr::corr_out(acc[i + 1][j], g),
+                                                       ofr::corr_out(acc[i + 2][j], g), ofr::corr_out(acc[i + 3][j], g)));
             } else {
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
                     const int x = xb + S2 * i;
-                    if (x < g.Wout) o[x] = acc[i][j] * g.scale;
+                    if (x < g.Wout) o[x] = ofr::corr_out(acc[i][j], g);
                 }
             }
         }
@@ -401,8 +402,16 @@ extern "C" size_t ofr_corr_workspace(int B, int C, int H, int W, int pad, int k,
 
 extern "C" int ofr_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int pad, int k,
                             int md, int s1, int s2, void* ws, size_t ws_bytes, ofr_stream_t stream) {
+    return ofr_corr_fwd_act(f1, f2, out, B, C, H, W, pad, k, md, s1, s2, 1.0f, ws, ws_bytes, stream);
+}
+
+extern "C" int ofr_corr_fwd_act(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int pad,
+                                int k, int md, int s1, int s2, float negative_slope, void* ws, size_t ws_bytes,
+                                ofr_stream_t stream) {
     CorrGeom g;
     if (!f1 || !f2 || !out || !make_geom(g, B, C, H, W, pad, k, md, s1, s2)) return OFR_EINVAL;
+    if (!(negative_slope >= 0.f)) return OFR_EINVAL;
+    g.slope = negative_slope;
     cudaStream_t st = (cudaStream_t)stream;
     if (polyphase_ok(g) && ws && !(reinterpret_cast<uintptr_t>(ws) & 255u) && ws_bytes >= poly_ws_bytes(g, false) &&
         ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(out)) {

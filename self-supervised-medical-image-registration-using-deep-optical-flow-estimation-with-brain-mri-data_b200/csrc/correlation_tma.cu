@@ -220,8 +220,8 @@ __global__ void __maxnreg__(224)
                 float* buf = wstage + boff + slot;
 #pragma unroll
                 for (int i = 0; i < M; i += 4)
-                    *reinterpret_cast<float4*>(buf + i) = make_float4(acc[i][j] * g.scale, acc[i + 1][j] * g.scale,
-                                                                      acc[i + 2][j] * g.scale, acc[i + 3][j] * g.scale);
+                    *reinterpret_cast<float4*>(buf + i) = make_float4(ofr::corr_out(acc[i][j], g), ofr::corr_out(acc[i + 1][j], g),
+                                                                      ofr::corr_out(acc[i + 2][j], g), ofr::corr_out(acc[i + 3][j], g));
                 __syncwarp(wmask);
 #pragma unroll
                 for (int k = 0; k < T::EPI; ++k) {
@@ -371,7 +371,7 @@ __global__ void __maxnreg__(224)
         const int y = y0 + ry, x = x0 + cx;
         if (y < g.Hout && x < g.Wout)
             __stcs(reinterpret_cast<float4*>(out + ((size_t)b * D * D + plane) * hw + (size_t)y * g.Wout + x),
-                   make_float4(sum.x * g.scale, sum.y * g.scale, sum.z * g.scale, sum.w * g.scale));
+                   make_float4(ofr::corr_out(sum.x, g), ofr::corr_out(sum.y, g), ofr::corr_out(sum.z, g), ofr::corr_out(sum.w, g)));
     }
     cluster.sync();  // remote shared memory must outlive the reads
 }

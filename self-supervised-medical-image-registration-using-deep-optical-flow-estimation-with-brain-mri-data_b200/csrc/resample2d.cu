@@ -43,6 +43,7 @@ namespace {
 struct WarpGeom {
     int B, C, Hin, Win, Hf, Wf;
     float fx, fy;  // STN: float32(2/W), float32(2/H)
+    float fs;      // the flow is multiplied by fs first (1 = plain call; PWCNet.py:214 passes flo * 0.625 ...)
 };
 
 struct Samp {
@@ -61,6 +62,8 @@ template <int MODE>
 __device__ __forceinline__ Samp make_samp(int x, int y, float u, float v, const WarpGeom& g) {
     Samp s;
     float ix, iy;
+    u = __fmul_rn(u, g.fs);  // exact identity for fs = 1
+    v = __fmul_rn(v, g.fs);
     if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) {
         ix = __fadd_rn((float)x, u);
         iy = __fadd_rn((float)y, v);
@@ -172,8 +175,8 @@ __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const floa
             const Samp s = make_samp<MODE>(x, y0 + k, u[k], v[k], g);
             live[k] = s.live;
             if (MODE == OFR_WARP_FLOWNET2_NEAREST) {  // nearest tap: floor(x + u + 0.5), clamped
-                const float xn = floorf(__fadd_rn(__fadd_rn((float)x, u[k]), 0.5f));
-                const float yn = floorf(__fadd_rn(__fadd_rn((float)(y0 + k), v[k]), 0.5f));
+                const float xn = floorf(__fadd_rn(__fadd_rn((float)x, __fmul_rn(u[k], g.fs)), 0.5f));
+                const float yn = floorf(__fadd_rn(__fadd_rn((float)(y0 + k), __fmul_rn(v[k], g.fs)), 0.5f));
                 const int xi = min(max(safe_floor_int(xn, g.Win), 0), g.Win - 1);
                 const int yi = min(max(safe_floor_int(yn, g.Hin), 0), g.Hin - 1);
                 t[k].tl = yi * g.Win + xi;
@@ -262,8 +265,8 @@ __global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const
 #pragma unroll
         for (int k = 0; k < kPX; ++k)
             if (ok[k]) {
-                __stcs(o + k * g.Wf, ax[k] * sx);
-                __stcs(o + hwf + k * g.Wf, ay[k] * sy);
+                __stcs(o + k * g.Wf, ax[k] * sx * g.fs);
+                __stcs(o + hwf + k * g.Wf, ay[k] * sy * g.fs);
             }
     }
 }
@@ -607,8 +610,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
         if (csplit == 1) {
             if (live) {
                 float* o = gI2 + (size_t)b * 2 * hwf + orem;
-                o[0] = ax * gsx;
-                o[hwf] = ay * gsy;
+                o[0] = ax * gsx * g.fs;
+                o[hwf] = ay * gsy * g.fs;
             }
         } else {
             // combine the channel splits of this tile through distributed shared memory, in rank order
@@ -624,8 +627,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                     syv += p[kTileThreads + tid];
                 }
                 float* o = gI2 + (size_t)b * 2 * hwf + orem;
-                o[0] = sxv * gsx;
-                o[hwf] = syv * gsy;
+                o[0] = sxv * gsx * g.fs;
+                o[hwf] = syv * gsy * g.fs;
             }
             cluster.sync();  // remote shared memory must outlive the reads
         }
@@ -657,8 +660,9 @@ bool geom_ok(int B, int C, int Hin, int Win, int Hf, int Wf) {
     return true;
 }
 
-WarpGeom make_geom(int B, int C, int Hin, int Win, int Hf, int Wf) {
+WarpGeom make_geom(int B, int C, int Hin, int Win, int Hf, int Wf, float fs) {
     WarpGeom g;
+    g.fs = fs;
     g.B = B, g.C = C, g.Hin = Hin, g.Win = Win, g.Hf = Hf, g.Wf = Wf;
     g.fx = (float)(2.0 / Win);  // models.py:264 builds a FloatTensor from the python floats 2/w, 2/h
     g.fy = (float)(2.0 / Hin);
@@ -756,9 +760,14 @@ int run_bwd(const float* in1, const float* flow, const float* gO, float* gI1, fl
 
 extern "C" int ofr_resample_fwd(const float* in1, const float* flow, float* out, int B, int C, int Hin, int Win,
                                 int Hf, int Wf, int mode, ofr_stream_t stream) {
+    return ofr_resample_fwd_scaled(in1, flow, out, B, C, Hin, Win, Hf, Wf, mode, 1.0f, stream);
+}
+
+extern "C" int ofr_resample_fwd_scaled(const float* in1, const float* flow, float* out, int B, int C, int Hin, int Win,
+                                       int Hf, int Wf, int mode, float flow_scale, ofr_stream_t stream) {
     if (!in1 || !flow || !out || !geom_ok(B, C, Hin, Win, Hf, Wf)) return OFR_EINVAL;
     if ((mode == OFR_WARP_STN || mode == OFR_WARP_PWC) && (Hin != Hf || Win != Wf)) return OFR_EINVAL;
-    const WarpGeom g = make_geom(B, C, Hin, Win, Hf, Wf);
+    const WarpGeom g = make_geom(B, C, Hin, Win, Hf, Wf, flow_scale);
     cudaStream_t st = (cudaStream_t)stream;
     switch (mode) {
         case OFR_WARP_FLOWNET2: return launch_fwd<OFR_WARP_FLOWNET2>(in1, flow, out, g, st);
@@ -778,6 +787,12 @@ extern "C" size_t ofr_resample_bwd_workspace(int B, int C, int Hin, int Win, int
 extern "C" int ofr_resample_bwd(const float* in1, const float* flow, const float* gO, float* gI1, float* gI2, int B,
                                 int C, int Hin, int Win, int Hf, int Wf, int mode, void* ws, size_t ws_bytes,
                                 ofr_stream_t stream) {
+    return ofr_resample_bwd_scaled(in1, flow, gO, gI1, gI2, B, C, Hin, Win, Hf, Wf, mode, 1.0f, ws, ws_bytes, stream);
+}
+
+extern "C" int ofr_resample_bwd_scaled(const float* in1, const float* flow, const float* gO, float* gI1, float* gI2,
+                                       int B, int C, int Hin, int Win, int Hf, int Wf, int mode, float flow_scale,
+                                       void* ws, size_t ws_bytes, ofr_stream_t stream) {
     if (!in1 || !flow || !gO || !geom_ok(B, C, Hin, Win, Hf, Wf)) return OFR_EINVAL;
     if (!gI1 && !gI2) return OFR_OK;
     if ((mode == OFR_WARP_STN || mode == OFR_WARP_PWC) && (Hin != Hf || Win != Wf)) return OFR_EINVAL;
@@ -786,7 +801,7 @@ extern "C" int ofr_resample_bwd(const float* in1, const float* flow, const float
         if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < ws_layout(B, Hf, Wf).total)
             return OFR_EWORKSPACE;
     }
-    const WarpGeom g = make_geom(B, C, Hin, Win, Hf, Wf);
+    const WarpGeom g = make_geom(B, C, Hin, Win, Hf, Wf, flow_scale);
     cudaStream_t st = (cudaStream_t)stream;
     switch (mode) {
         case OFR_WARP_FLOWNET2: return run_bwd<OFR_WARP_FLOWNET2>(in1, flow, gO, gI1, gI2, g, ws, st);

@@ -37,8 +37,12 @@ class PWCNetHost(nn.Module):
             setattr(self, f"conv{lvl}{second}", _conv(ch, ch))
             setattr(self, f"conv{lvl}b", _conv(ch, ch))
             cin = ch
+        # product path: LeakyReLU fused into the correlation store, flow pre-scale fused into the warp;
+        # injected layers (the CPU oracle in tests / bench reference arm) are followed by the separate ops, as in
+        # the reference
+        self._fused = corr is None and warp is None
         self.corr = corr if corr is not None else Correlation(pad_size=md, kernel_size=1, max_displacement=md,
-                                                              stride1=1, stride2=1, corr_multiply=1)
+                                                              stride1=1, stride2=1, corr_multiply=1, leaky_relu=0.1)
         self._warp = warp if warp is not None else pwc_warp
         self.leakyRELU = nn.LeakyReLU(0.1)
         nd = (2 * md + 1) ** 2
@@ -90,11 +94,13 @@ class PWCNetHost(nn.Module):
         dense = None
         for lvl in (6, 5, 4, 3, 2):
             if lvl == 6:
-                vol = self.leakyRELU(self.corr(f1[6], f2[6]))
-                inp = vol
+                vol = self.corr(f1[6], f2[6])
+                inp = vol if self._fused else self.leakyRELU(vol)
             else:
-                warped = self._warp(f2[lvl], up_flow * _FLOW_SCALE[lvl])
-                vol = self.leakyRELU(self.corr(f1[lvl], warped))
+                if self._fused:
+                    vol = self.corr(f1[lvl], self._warp(f2[lvl], up_flow, _FLOW_SCALE[lvl]))
+                else:
+                    vol = self.leakyRELU(self.corr(f1[lvl], self._warp(f2[lvl], up_flow * _FLOW_SCALE[lvl])))
                 inp = torch.cat((vol, f1[lvl], up_flow, up_feat), 1)
             dense, flows[lvl] = self._decode(lvl, inp)
             if lvl > 2:

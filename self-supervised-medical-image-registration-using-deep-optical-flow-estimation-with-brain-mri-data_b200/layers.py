@@ -61,7 +61,7 @@ def correlation_out_shape(H, W, pad_size, kernel_size, max_displacement, stride1
 
 class _CorrelationFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, input1, input2, pad, k, md, s1, s2):
+    def forward(ctx, input1, input2, pad, k, md, s1, s2, slope=None):
         input1, input2 = _prep(input1, "Correlation input1"), _prep(input2, "Correlation input2")
         if input1.shape != input2.shape:
             raise ValueError(f"Correlation: input shapes differ {tuple(input1.shape)} vs {tuple(input2.shape)}")
@@ -72,17 +72,25 @@ class _CorrelationFn(torch.autograd.Function):
         with torch.cuda.device(input1.device), region(f"corr_fwd C{C} {H}x{W} D{D}", nbytes, 2 * B * D * D * C * Ho * Wo):
             ws_bytes = int(_lib.lib().ofr_corr_workspace(B, C, H, W, pad, k, md, s1, s2, 0))
             ws = _workspace(ws_bytes, input1.device) if ws_bytes else None
-            _lib.check(_lib.lib().ofr_corr_fwd(_ptr(input1), _ptr(input2), _ptr(out), B, C, H, W, pad, k, md, s1, s2,
-                                               _ptr(ws), ws_bytes, _stream()), "ofr_corr_fwd")
-        ctx.save_for_backward(input1, input2)
+            _lib.check(_lib.lib().ofr_corr_fwd_act(_ptr(input1), _ptr(input2), _ptr(out), B, C, H, W, pad, k, md, s1, s2,
+                                                   1.0 if slope is None else float(slope), _ptr(ws), ws_bytes,
+                                                   _stream()), "ofr_corr_fwd")
+        if slope is None:
+            ctx.save_for_backward(input1, input2)
+        else:  # the activation's backward needs the sign of the (activated) output
+            ctx.save_for_backward(input1, input2, out)
         ctx.geom = (pad, k, md, s1, s2)
+        ctx.slope = slope
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        input1, input2 = ctx.saved_tensors
+        input1, input2 = ctx.saved_tensors[:2]
         pad, k, md, s1, s2 = ctx.geom
         B, C, H, W = input1.shape
+        if ctx.slope is not None:  # LeakyReLU backward: slope > 0, so sign(out) == sign(pre-activation)
+            out = ctx.saved_tensors[2]
+            grad_out = torch.where(out > 0, grad_out, grad_out * ctx.slope)
         grad_out = _prep(grad_out, "Correlation grad_output")
         g1 = torch.empty_like(input1) if ctx.needs_input_grad[0] else None
         g2 = torch.empty_like(input2) if ctx.needs_input_grad[1] else None
@@ -97,15 +105,22 @@ class _CorrelationFn(torch.autograd.Function):
                 _lib.check(_lib.lib().ofr_corr_bwd(_ptr(input1), _ptr(input2), _ptr(grad_out), _ptr(g1), _ptr(g2),
                                                    B, C, H, W, pad, k, md, s1, s2, _ptr(ws), ws_bytes, _stream()),
                            "ofr_corr_bwd")
-        return g1, g2, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None
 
 
 class Correlation(nn.Module):
     """Cost volume.  Same constructor as flownet2's ``Correlation`` (defaults included);
     ``corr_multiply`` is accepted and ignored, as upstream."""
 
-    def __init__(self, pad_size=0, kernel_size=0, max_displacement=0, stride1=1, stride2=2, corr_multiply=1):
+    def __init__(self, pad_size=0, kernel_size=0, max_displacement=0, stride1=1, stride2=2, corr_multiply=1, *,
+                 leaky_relu=None):
+        """``leaky_relu`` (keyword only, not in flownet2's signature): negative slope of a LeakyReLU fused into the
+        store of the cost volume -- the activation every reference call site applies next (PWCNet.py:201,
+        FlowNetC.py:89).  ``None`` = the plain layer."""
         super().__init__()
+        if leaky_relu is not None and not leaky_relu > 0:
+            raise ValueError("Correlation: leaky_relu must be a positive slope")
+        self.leaky_relu = leaky_relu
         self.pad_size = pad_size
         self.kernel_size = kernel_size
         self.max_displacement = max_displacement
@@ -115,7 +130,7 @@ class Correlation(nn.Module):
 
     def forward(self, input1, input2):
         return _CorrelationFn.apply(input1, input2, self.pad_size, self.kernel_size, self.max_displacement,
-                                    self.stride1, self.stride2)
+                                    self.stride1, self.stride2, self.leaky_relu)
 
     def extra_repr(self):
         return (f"pad_size={self.pad_size}, kernel_size={self.kernel_size}, max_displacement={self.max_displacement}, "
@@ -139,7 +154,7 @@ def spatial_correlation_sample(input1, input2, kernel_size=1, patch_size=1, stri
 # ------------------------------------------------------------------------------------------ warps
 class _WarpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, input1, flow, mode):
+    def forward(ctx, input1, flow, mode, flow_scale=1.0):
         input1, flow = _prep(input1, "warp input1"), _prep(flow, "warp flow")
         B, C, Hin, Win = input1.shape
         Bf, two, Hf, Wf = flow.shape
@@ -149,10 +164,11 @@ class _WarpFn(torch.autograd.Function):
             raise ValueError("warp: image and flow must have the same spatial size")
         out = torch.empty(B, C, Hf, Wf, dtype=torch.float32, device=input1.device)
         with torch.cuda.device(input1.device), region(f"warp_fwd m{mode} C{C} {Hf}x{Wf}", 4 * B * Hf * Wf * (2 * C + 2)):
-            _lib.check(_lib.lib().ofr_resample_fwd(_ptr(input1), _ptr(flow), _ptr(out), B, C, Hin, Win, Hf, Wf, mode,
-                                                   _stream()), "ofr_resample_fwd")
+            _lib.check(_lib.lib().ofr_resample_fwd_scaled(_ptr(input1), _ptr(flow), _ptr(out), B, C, Hin, Win, Hf, Wf,
+                                                          mode, float(flow_scale), _stream()), "ofr_resample_fwd")
         ctx.save_for_backward(input1, flow)
         ctx.mode = mode
+        ctx.flow_scale = float(flow_scale)
         return out
 
     @staticmethod
@@ -165,12 +181,12 @@ class _WarpFn(torch.autograd.Function):
         if mode == WARP_FLOWNET2_NEAREST:
             if need1:
                 raise NotImplementedError("Resample2d(bilinear=False): image gradient is not provided")
-            return None, (torch.zeros_like(flow) if need2 else None), None
+            return None, (torch.zeros_like(flow) if need2 else None), None, None
         grad_out = _prep(grad_out, "warp grad_output")
         g1 = torch.empty_like(input1) if need1 else None
         g2 = torch.empty_like(flow) if need2 else None
         if g1 is None and g2 is None:
-            return None, None, None
+            return None, None, None, None
         nbytes = 4 * B * Hf * Wf * (2 * C + 2 + (C if g1 is not None else 0) + (2 if g2 is not None else 0))
         with torch.cuda.device(input1.device), region(
                 f"warp_bwd m{mode} C{C} {Hf}x{Wf} gI1={int(g1 is not None)} gI2={int(g2 is not None)}", nbytes):
@@ -178,10 +194,10 @@ class _WarpFn(torch.autograd.Function):
             if g1 is not None:
                 ws_bytes = int(_lib.lib().ofr_resample_bwd_workspace(B, C, Hin, Win, Hf, Wf, mode))
                 ws = _workspace(ws_bytes, input1.device)
-            _lib.check(_lib.lib().ofr_resample_bwd(_ptr(input1), _ptr(flow), _ptr(grad_out), _ptr(g1), _ptr(g2),
-                                                   B, C, Hin, Win, Hf, Wf, mode, _ptr(ws), ws_bytes, _stream()),
-                       "ofr_resample_bwd")
-        return g1, g2, None
+            _lib.check(_lib.lib().ofr_resample_bwd_scaled(_ptr(input1), _ptr(flow), _ptr(grad_out), _ptr(g1), _ptr(g2),
+                                                          B, C, Hin, Win, Hf, Wf, mode, ctx.flow_scale, _ptr(ws), ws_bytes,
+                                                          _stream()), "ofr_resample_bwd")
+        return g1, g2, None, None
 
 
 class Resample2d(nn.Module):
@@ -208,10 +224,12 @@ def stn_warp(flow, frame):
     return _WarpFn.apply(frame, flow, WARP_STN)
 
 
-def pwc_warp(x, flo):
+def pwc_warp(x, flo, flow_scale=1.0):
     """``PWCDCNet.warp(x, flo)`` (PWC/models/PWCNet.py:143-179) in one pass: sample, build the
-    ones-mask, threshold at 0.9999 and multiply, without materialising grid or mask."""
-    return _WarpFn.apply(x, flo, WARP_PWC)
+    ones-mask, threshold at 0.9999 and multiply, without materialising grid or mask.
+    ``pwc_warp(x, flo, s)`` == ``pwc_warp(x, flo * s)`` (the call sites ``:214,228,242,258`` pre-scale the
+    upsampled flow by 0.625 ... 5.0) without the extra elementwise pass."""
+    return _WarpFn.apply(x, flo, WARP_PWC, flow_scale)
 
 
 # ------------------------------------------------------------------------------------------ ChannelNorm

@@ -249,6 +249,45 @@ def test_warp_backward_degenerate_flows(ofr, kind):
         close(g1, rg, atol=1e-5, rtol=2e-4, what=f"{name} {kind} dImg")
 
 
+# =============================================================================== fused epilogues
+@pytest.mark.parametrize("tag", ["pwc_l6", "pwc_l4", "pwc_l2", "flownetc_small", "generic_w_odd"])
+def test_correlation_fused_leaky_relu(ofr, tag):
+    """Correlation(..., leaky_relu=0.1) == LeakyReLU(0.1)(Correlation(...)) (PWCNet.py:200-201), values and gradients."""
+    B, C, H, W, pad, k, md, s1, s2 = CORR_CASES[tag]
+    a = torch.randn(B, C, H, W, generator=gen(30)).to(DEV)
+    b = torch.randn(B, C, H, W, generator=gen(31)).to(DEV)
+    outs, grads = [], []
+    for fused in (False, True):
+        x, y = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        layer = ofr.Correlation(pad, k, md, s1, s2, 1, leaky_relu=0.1 if fused else None)
+        out = layer(x, y)
+        if not fused:
+            out = torch.nn.functional.leaky_relu(out, 0.1)
+        go = torch.randn(out.shape, generator=gen(32)).to(DEV)
+        outs.append(out.detach())
+        grads.append(torch.autograd.grad(out, (x, y), go))
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0] < 0).any()
+    for g0, g1 in zip(grads[0], grads[1]):
+        assert torch.equal(g0, g1)
+
+
+def test_pwc_warp_fused_flow_scale(ofr):
+    """pwc_warp(x, flo, s) == pwc_warp(x, flo * s) (PWCNet.py:214 passes `up_flow * 0.625`), values and gradients."""
+    B, C, H, W = 2, 24, 32, 32
+    x = torch.randn(B, C, H, W, generator=gen(33)).to(DEV)
+    fl = (torch.randn(B, 2, H, W, generator=gen(34)) * 2).to(DEV)
+    go = torch.randn(B, C, H, W, generator=gen(35)).to(DEV)
+    res = []
+    for fused in (False, True):
+        xi, fi = x.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+        out = ofr.pwc_warp(xi, fi, 2.5) if fused else ofr.pwc_warp(xi, fi * 2.5)
+        res.append((out.detach(),) + torch.autograd.grad(out, (xi, fi), go))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    close(res[1][2], res[0][2], atol=1e-6, rtol=1e-6, what="flow gradient through the fused scale")
+
+
 # =============================================================================== loss
 def test_loss_vs_reference_golden(ofr, golden):
     g = golden("loss")
