@@ -522,7 +522,7 @@ struct SweepAll {
 template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
 __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const CUtensorMap& mapG,
                                                   float* __restrict__ gI, const CorrGeom& g, int tiles_x, int tiles_y,
-                                                  int cblocks) {
+                                                  int cblocks, int ndir) {
     using T = BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
     constexpr int D = T::D;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -542,7 +542,7 @@ __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const
         x0 = txi * T::TW, y0 = tyi * TH, c0 = cbi * CB;
     };
     int x0, y0, c0, b;
-    decode(blockIdx.x, x0, y0, c0, b);
+    decode(blockIdx.x / ndir, x0, y0, c0, b);
 
     // lanes: rows (fastest) x strips of ONE channel group; warps: channel groups.  A quarter-warp reads 8 different rows
     // of the feature / gradient tiles, whose pitches are 4*odd (mod 32): conflict-free 128-bit LDS; and the 32-byte
@@ -629,20 +629,20 @@ __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const
     }
 }
 
-// Both gradients in ONE launch: blockIdx.y picks the direction (0: gI1 from f2, 1: gI2 from f1).  The two CTAs that
-// stream the same gradient planes run close together (the second read is an L2 hit), and on small maps the fixed
-// launch / first-load latency is paid once instead of twice.  `first` = direction of blockIdx.y == 0 when only one
-// gradient is wanted.
+// Both gradients in ONE launch: the lowest bit of blockIdx.x picks the direction (0: gI1 from f2, 1: gI2 from f1), so
+// the two CTAs that stream the same gradient planes are neighbours in launch order and the second read is an L2 hit
+// (with the direction on blockIdx.y ncu still showed the planes read twice from DRAM); on small maps the fixed
+// launch / first-load latency is paid once instead of twice.  `first` = the direction when only one gradient is wanted.
 template <int R, int TH, int NS, int CG, int TIC, int NSTG, int CB>
 __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, true, NSTG, CB>::THREADS, 1)
     corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapG0,
                         const __grid_constant__ CUtensorMap mapF1, const __grid_constant__ CUtensorMap mapG1,
                         float* __restrict__ gI1, float* __restrict__ gI2, CorrGeom g, int tiles_x, int tiles_y,
-                        int cblocks, int first) {
-    if ((int)blockIdx.y + first == 0)
-        corr_bwd_tma_body<R, TH, NS, CG, TIC, false, NSTG, CB>(mapF2, mapG0, gI1, g, tiles_x, tiles_y, cblocks);
+                        int cblocks, int ndir, int first) {
+    if ((int)(blockIdx.x % ndir) + first == 0)
+        corr_bwd_tma_body<R, TH, NS, CG, TIC, false, NSTG, CB>(mapF2, mapG0, gI1, g, tiles_x, tiles_y, cblocks, ndir);
     else
-        corr_bwd_tma_body<R, TH, NS, CG, TIC, true, NSTG, CB>(mapF1, mapG1, gI2, g, tiles_x, tiles_y, cblocks);
+        corr_bwd_tma_body<R, TH, NS, CG, TIC, true, NSTG, CB>(mapF1, mapG1, gI2, g, tiles_x, tiles_y, cblocks, ndir);
 }
 
 template <int R, int TH, int NS, int CG, int TIC, int NSTG, int CB>
@@ -661,11 +661,11 @@ int launch_bwd(const float* f1, const float* f2, const float* gO, float* gI1, fl
     const int tiles_x = (g.W + T0::TW - 1) / T0::TW, tiles_y = (g.H + TH - 1) / TH;
     const int cblocks = (g.C + CB - 1) / CB;
     const long long nblk = (long long)tiles_x * tiles_y * cblocks * g.B;
-    if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
+    if (nblk >= (1ll << 30)) return OFR_ENOTSUP;
     const int ndir = (gI1 ? 1 : 0) + (gI2 ? 1 : 0);
     if (ndir == 0) return OFR_OK;
-    dim3 grid((unsigned)nblk, (unsigned)ndir);
-    kern<<<grid, T0::THREADS, smem, st>>>(mF2, mG0, mF1, mG1, gI1, gI2, g, tiles_x, tiles_y, cblocks, gI1 ? 0 : 1);
+    kern<<<(unsigned)(nblk * ndir), T0::THREADS, smem, st>>>(mF2, mG0, mF1, mG1, gI1, gI2, g, tiles_x, tiles_y, cblocks,
+                                                              ndir, gI1 ? 0 : 1);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
