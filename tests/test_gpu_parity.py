@@ -378,3 +378,119 @@ def test_pwcnet_training_step_matches_oracle_layers(ofr):
             assert rel < 2e-2, (name, rel)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+# =============================================================================== no out-of-bounds writes
+class _Guarded:
+    """A float32 device buffer of `n` elements framed by two guard zones filled with a sentinel; every output and
+    workspace of a raw C-ABI call is allocated through it, and `check()` asserts the guards are untouched."""
+    PAD = 4096  # elements on each side (16 KB), keeps the payload 256-byte aligned
+
+    def __init__(self, n, dtype=torch.float32):
+        self.n, self.dtype = int(n), dtype
+        self.buf = torch.full((self.n + 2 * self.PAD,), 12345.0, dtype=torch.float32, device=DEV).to(dtype)
+        self.sentinel = self.buf[0].clone()
+
+    @property
+    def t(self):
+        return self.buf[self.PAD:self.PAD + self.n]
+
+    def ptr(self):
+        import ctypes
+        return ctypes.c_void_p(self.t.data_ptr())
+
+    def check(self, what):
+        lo, hi = self.buf[:self.PAD], self.buf[self.PAD + self.n:]
+        assert bool((lo == self.sentinel).all()) and bool((hi == self.sentinel).all()), f"{what}: guard zone overwritten"
+
+
+@pytest.mark.parametrize("shape", [(2, 13, 12, 20), (1, 8, 6, 136), (2, 196, 4, 4), (3, 40, 16, 16), (1, 32, 30, 36)])
+def test_correlation_writes_stay_inside_their_buffers(ofr, shape):
+    """Raw C-ABI calls with guard zones around every written buffer (TMA kernels, cluster split, ragged tiles)."""
+    import ctypes
+    from ofr_b200 import _lib
+    L = _lib.lib()
+    B, C, H, W = shape
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    f1 = torch.randn(B, C, H, W, generator=gen(40)).to(DEV)
+    f2 = torch.randn(B, C, H, W, generator=gen(41)).to(DEV)
+    out, g1, g2 = _Guarded(B * 81 * H * W), _Guarded(B * C * H * W), _Guarded(B * C * H * W)
+    assert L.ofr_corr_fwd_act(P(f1), P(f2), out.ptr(), B, C, H, W, 4, 1, 4, 1, 1, 0.1, None, 0, st) == 0
+    go = torch.randn(B, 81, H, W, generator=gen(42)).to(DEV)
+    assert L.ofr_corr_bwd(P(f1), P(f2), P(go), g1.ptr(), g2.ptr(), B, C, H, W, 4, 1, 4, 1, 1, None, 0, st) == 0
+    torch.cuda.synchronize()
+    for name, gbuf in (("corr out", out), ("corr gI1", g1), ("corr gI2", g2)):
+        gbuf.check(name)
+        assert bool(torch.isfinite(gbuf.t).all()) and not bool((gbuf.t == 12345.0).any()), f"{name}: unwritten elements"
+    ref = torch.nn.functional.leaky_relu(oracle.correlation(f1.cpu().double(), f2.cpu().double(), 4, 1, 4, 1, 1), 0.1)
+    close(out.t.view(B, 81, H, W), ref, atol=1e-5, what="guarded corr fwd")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(2, 5, 9, 13), (1, 24, 32, 32), (2, 1, 40, 36), (1, 130, 8, 8)])
+def test_warp_writes_stay_inside_their_buffers(ofr, mode, shape):
+    import ctypes
+    from ofr_b200 import _lib
+    L = _lib.lib()
+    B, C, H, W = shape
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x = torch.randn(B, C, H, W, generator=gen(43)).to(DEV)
+    fl = (torch.randn(B, 2, H, W, generator=gen(44)) * 3).to(DEV)
+    go = torch.randn(B, C, H, W, generator=gen(45)).to(DEV)
+    out, g1, g2 = _Guarded(B * C * H * W), _Guarded(B * C * H * W), _Guarded(B * 2 * H * W)
+    nws = int(L.ofr_resample_bwd_workspace(B, C, H, W, H, W, mode))
+    ws = _Guarded((nws + 3) // 4)
+    assert L.ofr_resample_fwd_scaled(P(x), P(fl), out.ptr(), B, C, H, W, H, W, mode, 1.25, st) == 0
+    assert L.ofr_resample_bwd_scaled(P(x), P(fl), P(go), g1.ptr(), g2.ptr(), B, C, H, W, H, W, mode, 1.25, ws.ptr(),
+                                     nws, st) == 0
+    g2b = _Guarded(B * 2 * H * W)  # flow gradient only: the other kernel family
+    assert L.ofr_resample_bwd_scaled(P(x), P(fl), P(go), None, g2b.ptr(), B, C, H, W, H, W, mode, 1.25, None, 0, st) == 0
+    torch.cuda.synchronize()
+    for name, gbuf in (("warp out", out), ("warp gI1", g1), ("warp gI2", g2), ("warp workspace", ws), ("warp gI2'", g2b)):
+        gbuf.check(f"{name} mode {mode}")
+    for name, gbuf in (("warp out", out), ("warp gI1", g1), ("warp gI2", g2), ("warp gI2'", g2b)):
+        assert not bool((gbuf.t == 12345.0).any()), f"{name}: unwritten elements"
+    close(g2b.t, g2.t, atol=1e-5, rtol=1e-4, what="flow gradient: fused kernel vs flow-only kernel")
+
+
+def test_loss_and_channelnorm_writes_stay_inside_their_buffers(ofr):
+    import ctypes
+    from ofr_b200 import _lib
+    L = _lib.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    B, S = 3, 40
+    sizes = [(40, 40), (20, 20), (10, 12), (5, 7)]
+    fixed = torch.rand(B, 1, S, S, generator=gen(46)).to(DEV)
+    flows = [torch.randn(B, 2, h, w, generator=gen(47)).to(DEV) for h, w in sizes]
+    warps = [torch.rand(B, 1, h, w, generator=gen(48)).to(DEV) for h, w in sizes]
+    gfl = [_Guarded(B * 2 * h * w) for h, w in sizes]
+    gwp = [_Guarded(B * h * w) for h, w in sizes]
+    n = len(sizes)
+    arr = (_lib.LossScale * n)()
+    for i, (h, w) in enumerate(sizes):
+        arr[i].warped, arr[i].flow = warps[i].data_ptr(), flows[i].data_ptr()
+        arr[i].g_warped, arr[i].g_flow = gwp[i].t.data_ptr(), gfl[i].t.data_ptr()
+        arr[i].h, arr[i].w = h, w
+    out4, state = _Guarded(4, torch.float64), _Guarded(n * 16, torch.float64)
+    nws = int(L.ofr_loss_workspace(n))
+    ws = _Guarded((nws + 3) // 4)
+    g4 = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=DEV)
+    assert L.ofr_loss_fwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, out4.ptr(), state.ptr(), ws.ptr(), nws, st) == 0
+    assert L.ofr_loss_bwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(g4), state.ptr(), st) == 0
+    x = torch.randn(2, 3, 7, 9, generator=gen(49)).to(DEV)
+    o, gi = _Guarded(2 * 7 * 9), _Guarded(x.numel())
+    gout = torch.randn(2, 1, 7, 9, generator=gen(50)).to(DEV)
+    assert L.ofr_chnorm_fwd(P(x), o.ptr(), 2, 3, 7, 9, st) == 0
+    assert L.ofr_chnorm_bwd(P(x), o.ptr(), P(gout), gi.ptr(), 2, 3, 7, 9, st) == 0
+    torch.cuda.synchronize()
+    for i in range(n):
+        gfl[i].check(f"loss g_flow[{i}]")
+        gwp[i].check(f"loss g_warped[{i}]")
+        assert not bool((gfl[i].t == 12345.0).any()) and not bool((gwp[i].t == 12345.0).any())
+    for name, gbuf in (("loss out4", out4), ("loss state", state), ("loss workspace", ws), ("chnorm out", o), ("chnorm gI", gi)):
+        gbuf.check(name)
+    ref = oracle.ofe_loss([f.cpu() for f in flows], [w.cpu() for w in warps], fixed.cpu())
+    np.testing.assert_allclose(out4.t.cpu().numpy(), [float(r) for r in ref], rtol=2e-6)
