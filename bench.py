@@ -32,6 +32,13 @@ import torch.distributed as dist  # noqa: E402
 METRIC = "PWC-Net train slice-pairs/s @1/2/4/8 B200; corr+warp kernel % of roofline"
 UNIT = "slice-pairs/s"
 FMA_PEAK_TFLOPS = 72.3  # measured: profiles/r01_fma_peak.txt
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of tools/opbench.py at the bench's
+# shapes (B = 24, S = 512); keyed by the label of the C-ABI call
+NCU_TRAFFIC_BYTES = {
+    "corr_bwd C32 128x128 D2=81 g2": (228.1e6 + 77.4e6, "profiles/r01_u_ncu_corr_bwd.txt"),
+    "corr_fwd C32 128x128 D9": (100.8e6 + 73.7e6, "profiles/r01_o_ncu_corr_fwd.txt"),
+    "warp_bwd m2 C32 128x128 gI1=1 gI2=1": (107.0e6 + 30.9e6 + 3.2e6, "profiles/r01_t_ncu_corr_bwd_warp_bwd.txt"),
+}
 
 
 def peaks():
@@ -237,7 +244,10 @@ def run_ours(args):
         ours_ms = sum(r["avg_us"] * r["calls_per_step"] for r in rows) * 1e-3
         dom = rows[0]
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": round(dom["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(dom["gbs"] / peak, 4),
+                    "traffic": NCU_TRAFFIC_BYTES.get(dom["kernel"], (None, None))[0],
+                    "traffic_source": NCU_TRAFFIC_BYTES.get(dom["kernel"], (None, None))[1],
+                    "algorithmic_bytes": dom["algorithmic_bytes"], "peak_source": peak_src,
                     "avg_launch_us": dom["avg_us"], "tflops_fp32": dom["tflops"],
                     "fp32_fma_peak_tflops": FMA_PEAK_TFLOPS, "fp32_fma_frac": round(dom["tflops"] / FMA_PEAK_TFLOPS, 4),
                     "fp32_fma_peak_source": "measured on this pool's B200 with tools/micro/fma_peak.cu (d = a*b + d, "
