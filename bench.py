@@ -5,7 +5,7 @@
 
 Workload ``pwcnet_train``: one self-supervised PWC-Net training step per "step" on synthetic brain-slice
 pairs -- host model (cuDNN convolutions) around the ofr_b200 hot path: 5x Correlation(4,1,4,1,1) fwd+bwd,
-4x pwc_warp fwd+bwd, 7x stn warp fwd+bwd, the fused 7-scale OFEloss fwd+bwd -- then Adam.  This is
+4x pwc_warp fwd+bwd, the 7 stn warps (one batched launch each way), the fused 7-scale OFEloss fwd+bwd -- then Adam.  This is
 BASELINE.json configs[2] (PWC-Net, batch 24 per GPU, 512x512) and, over N GPUs, configs[4] (DDP, one
 NCCL gradient all-reduce per step).  Rank 0 prints ONE JSON line.
 
@@ -104,7 +104,7 @@ def build_gpu_step(device, channels_last=False):
     if channels_last:  # host-model memory format only; the ofr_b200 layers take / return NCHW (they call .contiguous())
         host = host.to(memory_format=torch.channels_last)
     host.deconv0.requires_grad_(False)  # unused in the forward (PWCNet.py:126,274): keep it out of DDP's reducer
-    return RegistrationStep(host, ofr.stn_warp, ofr.OFEloss), ofr
+    return RegistrationStep(host, ofr.stn_warp, ofr.OFEloss, stn_multi=ofr.stn_warp_multi), ofr
 
 
 def build_cpu_step():

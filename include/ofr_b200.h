@@ -133,6 +133,22 @@ int ofr_resample_bwd_scaled(const float* in1, const float* flow, const float* gO
                      int B, int C, int Hin, int Win, int Hf, int Wf, int mode, float flow_scale,
                      void* ws, size_t ws_bytes, ofr_stream_t stream);
 
+/* ------------------------------------------------------------------ multi-scale stn
+ * The loop `for flow in flows: stn(flow, frame)` of opticalFlowReg.forward (models.py:277-281) in one launch
+ * each way.  frame_i is the frame already resized to flow_i's size ([B,C,h,w]); out_i = stn(flow_i, frame_i).
+ * Backward writes the flow gradients only (the frame is an input image and needs none). */
+#define OFR_STN_MAX_SCALES 8
+typedef struct {
+    const float* frame;  /* [B,C,h,w] */
+    const float* flow;   /* [B,2,h,w] */
+    float* out;          /* forward:  [B,C,h,w]                 */
+    const float* g_out;  /* backward: [B,C,h,w]                 */
+    float* g_flow;       /* backward: [B,2,h,w]                 */
+    int h, w;
+} ofr_stn_scale_t;
+int ofr_stn_multi_fwd(const ofr_stn_scale_t* scales, int n_scales, int B, int C, ofr_stream_t stream);
+int ofr_stn_multi_bwd(const ofr_stn_scale_t* scales, int n_scales, int B, int C, ofr_stream_t stream);
+
 /* ------------------------------------------------------------------ ChannelNorm
  * Replaces ChannelNorm().forward/backward -- flownet2/models.py:40,141..180.
  *   out[b,0,y,x] = sqrt(sum_c x[b,c,y,x]^2);   gI = gO * x / (out + 1e-8).

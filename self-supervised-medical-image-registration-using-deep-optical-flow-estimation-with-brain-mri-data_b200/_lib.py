@@ -33,6 +33,15 @@ class LossScale(ctypes.Structure):
                 ("h", ctypes.c_int), ("w", ctypes.c_int)]
 
 
+class StnScale(ctypes.Structure):
+    """Mirror of ``ofr_stn_scale_t``."""
+    _fields_ = [("frame", ctypes.c_void_p), ("flow", ctypes.c_void_p), ("out", ctypes.c_void_p),
+                ("g_out", ctypes.c_void_p), ("g_flow", ctypes.c_void_p), ("h", ctypes.c_int), ("w", ctypes.c_int)]
+
+
+STN_MAX_SCALES = 8
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -81,6 +90,8 @@ def _declare(lib):
         "ofr_resample_bwd_scaled": (c_int, [vp, vp, vp, vp, vp] + [c_int] * 7 + [ctypes.c_float, vp, c_size_t, vp]),
         "ofr_resample_bwd_workspace": (c_size_t, [c_int] * 7),
         "ofr_resample_bwd": (c_int, [vp, vp, vp, vp, vp] + [c_int] * 7 + [vp, c_size_t, vp]),
+        "ofr_stn_multi_fwd": (c_int, [ctypes.POINTER(StnScale), c_int, c_int, c_int, vp]),
+        "ofr_stn_multi_bwd": (c_int, [ctypes.POINTER(StnScale), c_int, c_int, c_int, vp]),
         "ofr_chnorm_fwd": (c_int, [vp, vp] + [c_int] * 4 + [vp]),
         "ofr_chnorm_bwd": (c_int, [vp, vp, vp, vp] + [c_int] * 4 + [vp]),
         "ofr_loss_workspace": (c_size_t, [c_int]),
@@ -99,7 +110,7 @@ def _declare(lib):
 EXPORTS = ["ofr_abi_version", "ofr_error_string", "ofr_launch_count", "ofr_corr_out_shape", "ofr_corr_workspace",
            "ofr_corr_fwd", "ofr_corr_fwd_act",
            "ofr_corr_bwd", "ofr_resample_fwd", "ofr_resample_fwd_scaled", "ofr_resample_bwd_workspace", "ofr_resample_bwd",
-           "ofr_resample_bwd_scaled",
+           "ofr_resample_bwd_scaled", "ofr_stn_multi_fwd", "ofr_stn_multi_bwd",
            "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd"]
 
 

@@ -145,21 +145,17 @@ constexpr int kPX = 4;        // pixels per thread, stacked in a column
 // smooth flows; four pixels per thread along x would spread every request over four lines and make the L1 tag stage the
 // bottleneck).  A thread owns kPX vertically adjacent pixels: rows y0 .. y0+kPX-1, whose tap rows overlap in L1.
 // blockIdx.z = image * nchunks + channel chunk.
+// pixels (x, y0 .. y0+kPX-1) of image b, channels [c0, c1)
 template <int MODE>
-__global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const float* __restrict__ in1,
-                                                                      const float* __restrict__ flow,
-                                                                      float* __restrict__ out, WarpGeom g, int nchunks) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
-    if (x >= g.Wf || y0 >= g.Hf) return;
+__device__ __forceinline__ void warp_fwd_body(const float* __restrict__ in1, const float* __restrict__ flow,
+                                              float* __restrict__ out, const WarpGeom& g, int x, int y0, int b, int c0,
+                                              int c1) {
     const int hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
     const int rem = y0 * g.Wf + x;
     bool ok[kPX];
 #pragma unroll
     for (int k = 0; k < kPX; ++k) ok[k] = y0 + k < g.Hf;
-    for (int z = blockIdx.z; z < g.B * nchunks; z += gridDim.z) {
-        const int b = z / nchunks, chunk = z - b * nchunks;
-        const int c0 = chunk * kFwdChunk, c1 = min(c0 + kFwdChunk, g.C);
+    {
         const float* fu = flow + (size_t)b * 2 * hwf + rem;
         float u[kPX], v[kPX];
 #pragma unroll
@@ -212,24 +208,34 @@ __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const floa
     }
 }
 
+
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const float* __restrict__ in1,
+                                                                      const float* __restrict__ flow,
+                                                                      float* __restrict__ out, WarpGeom g, int nchunks) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
+    if (x >= g.Wf || y0 >= g.Hf) return;
+    for (int z = blockIdx.z; z < g.B * nchunks; z += gridDim.z) {
+        const int b = z / nchunks, chunk = z - b * nchunks;
+        const int c0 = chunk * kFwdChunk;
+        warp_fwd_body<MODE>(in1, flow, out, g, x, y0, b, c0, min(c0 + kFwdChunk, g.C));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ backward: flow only
 // gI2 only (the image needs no gradient: opticalFlowReg.stn on the moving image, FlowNet2's Resample2d on the input
 // images).  Same thread mapping as the forward; channels looped in the thread.
 template <int MODE>
-__global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const float* __restrict__ in1,
-                                                                           const float* __restrict__ flow,
-                                                                           const float* __restrict__ gO,
-                                                                           float* __restrict__ gI2, WarpGeom g,
-                                                                           float sx, float sy) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
-    if (x >= g.Wf || y0 >= g.Hf) return;
+__device__ __forceinline__ void warp_bwd_flow_body(const float* __restrict__ in1, const float* __restrict__ flow,
+                                                   const float* __restrict__ gO, float* __restrict__ gI2,
+                                                   const WarpGeom& g, float sx, float sy, int x, int y0, int b) {
     const int hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
     const int rem = y0 * g.Wf + x;
     bool ok[kPX];
 #pragma unroll
     for (int k = 0; k < kPX; ++k) ok[k] = y0 + k < g.Hf;
-    for (int b = blockIdx.z; b < g.B; b += gridDim.z) {
+    {
         const float* fu = flow + (size_t)b * 2 * hwf + rem;
         float u[kPX], v[kPX];
 #pragma unroll
@@ -269,6 +275,56 @@ __global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const
                 __stcs(o + hwf + k * g.Wf, ay[k] * sy * g.fs);
             }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const float* __restrict__ in1,
+                                                                           const float* __restrict__ flow,
+                                                                           const float* __restrict__ gO,
+                                                                           float* __restrict__ gI2, WarpGeom g,
+                                                                           float sx, float sy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
+    if (x >= g.Wf || y0 >= g.Hf) return;
+    for (int b = blockIdx.z; b < g.B; b += gridDim.z) warp_bwd_flow_body<MODE>(in1, flow, gO, gI2, g, sx, sy, x, y0, b);
+}
+
+// ------------------------------------------------------------------------------------------------ multi-scale stn
+// The per-scale stn warps of opticalFlowReg.forward (models.py:277-281: one stn(flow_i, frame) per pyramid scale) in ONE
+// launch each way: most scales are a few thousand pixels, where a launch per scale is pure latency.  CTA = 32 x 32
+// pixels of one image of one scale; the per-thread work is the single-scale kernels' bodies.
+struct StnScale {
+    const float* frame;
+    const float* flow;
+    float* out;
+    const float* g_out;
+    float* g_flow;
+    WarpGeom g;
+    float sx, sy;
+    int tiles_x, tiles_y, cta_begin;
+};
+struct StnParams {
+    int n, cta_end;
+    StnScale sc[OFR_STN_MAX_SCALES];
+};
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kFwdThreads, 3) stn_multi_kernel(const __grid_constant__ StnParams p) {
+    int s = 0;
+    while (s + 1 < p.n && (int)blockIdx.x >= p.sc[s + 1].cta_begin) ++s;
+    const StnScale& sc = p.sc[s];
+    int t = blockIdx.x - sc.cta_begin;
+    const int per = sc.tiles_x * sc.tiles_y;
+    const int b = t / per;
+    t -= b * per;
+    const int ty = t / sc.tiles_x, tx = t - ty * sc.tiles_x;
+    const int x = tx * 32 + (threadIdx.x & 31);
+    const int y0 = (ty * (kFwdThreads / 32) + (threadIdx.x >> 5)) * kPX;
+    if (x >= sc.g.Wf || y0 >= sc.g.Hf) return;
+    if (BACKWARD)
+        warp_bwd_flow_body<OFR_WARP_STN>(sc.frame, sc.flow, sc.g_out, sc.g_flow, sc.g, sc.sx, sc.sy, x, y0, b);
+    else
+        warp_fwd_body<OFR_WARP_STN>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, sc.g.C);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: image (+ flow)
@@ -674,7 +730,9 @@ WarpGeom make_geom(int B, int C, int Hin, int Win, int Hf, int Wf, float fs) {
 void block_shape(int W, int H, dim3& block, dim3& grid, unsigned gz) {
     int bx = 8;
     while (bx < W && bx < 32) bx <<= 1;
-    const int by = kFwdThreads / bx;
+    int by = kFwdThreads / bx;
+    const int need = (H + kPX - 1) / kPX;  // small maps: no thread rows beyond the image
+    if (by > need) by = need;
     block = dim3(bx, by);
     grid = dim3((W + bx - 1) / bx, (H + by * kPX - 1) / (by * kPX), gz);
 }
@@ -809,4 +867,46 @@ extern "C" int ofr_resample_bwd_scaled(const float* in1, const float* flow, cons
         case OFR_WARP_PWC: return run_bwd<OFR_WARP_PWC>(in1, flow, gO, gI1, gI2, g, ws, st);
         default: return OFR_EINVAL;
     }
+}
+
+namespace {
+
+int stn_multi(const ofr_stn_scale_t* scales, int n, int B, int C, bool backward, cudaStream_t st) {
+    if (!scales || n < 1 || n > OFR_STN_MAX_SCALES || B <= 0 || C <= 0) return OFR_EINVAL;
+    StnParams p;
+    p.n = n;
+    long long at = 0;
+    for (int i = 0; i < n; ++i) {
+        const ofr_stn_scale_t& s = scales[i];
+        if (!s.frame || !s.flow || !geom_ok(B, C, s.h, s.w, s.h, s.w)) return OFR_EINVAL;
+        if (backward ? (!s.g_out || !s.g_flow) : !s.out) return OFR_EINVAL;
+        StnScale& d = p.sc[i];
+        d.frame = s.frame, d.flow = s.flow, d.out = s.out, d.g_out = s.g_out, d.g_flow = s.g_flow;
+        d.g = make_geom(B, C, s.h, s.w, s.h, s.w, 1.0f);
+        d.sx = (0.5f * (float)(s.w - 1)) * d.g.fx;  // chain factors of the stn grid, as in run_bwd
+        d.sy = (0.5f * (float)(s.h - 1)) * d.g.fy;
+        d.tiles_x = (s.w + 31) / 32;
+        d.tiles_y = (s.h + (kFwdThreads / 32) * kPX - 1) / ((kFwdThreads / 32) * kPX);
+        d.cta_begin = (int)at;
+        at += (long long)d.tiles_x * d.tiles_y * B;
+        if (at >= (1ll << 31)) return OFR_ENOTSUP;
+    }
+    for (int i = n; i < OFR_STN_MAX_SCALES; ++i) p.sc[i] = p.sc[n - 1];
+    p.cta_end = (int)at;
+    if (backward)
+        stn_multi_kernel<true><<<(unsigned)at, kFwdThreads, 0, st>>>(p);
+    else
+        stn_multi_kernel<false><<<(unsigned)at, kFwdThreads, 0, st>>>(p);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+}  // namespace
+
+extern "C" int ofr_stn_multi_fwd(const ofr_stn_scale_t* scales, int n_scales, int B, int C, ofr_stream_t stream) {
+    return stn_multi(scales, n_scales, B, C, false, (cudaStream_t)stream);
+}
+
+extern "C" int ofr_stn_multi_bwd(const ofr_stn_scale_t* scales, int n_scales, int B, int C, ofr_stream_t stream) {
+    return stn_multi(scales, n_scales, B, C, true, (cudaStream_t)stream);
 }

@@ -56,17 +56,22 @@ def synthetic_pairs(batch, size, seed=6, device="cpu", max_shift=8.0):
 class RegistrationStep(nn.Module):
     """predictor + per-scale stn warp + multi-scale loss; ``forward(pair)`` returns (p, c, s, total)."""
 
-    def __init__(self, predictor, stn, loss_fn):
+    def __init__(self, predictor, stn, loss_fn, stn_multi=None):
+        """``stn_multi(flows, moving)`` (optional) replaces the per-scale ``stn`` loop with one batched call."""
         super().__init__()
         self.predictor = predictor
         self._stn = stn
+        self._stn_multi = stn_multi
         self._loss = loss_fn
 
     def forward(self, pair):
         flows = list(self.predictor(pair))
         fixed = pair[:, :1].contiguous()
         moving = pair[:, 1:].contiguous()
-        warped = [self._stn(flow, moving) for flow in flows]
+        if self._stn_multi is not None:
+            warped = self._stn_multi(flows, moving)
+        else:
+            warped = [self._stn(flow, moving) for flow in flows]
         return self._loss(flows, warped, fixed)
 
 

@@ -224,6 +224,75 @@ def stn_warp(flow, frame):
     return _WarpFn.apply(frame, flow, WARP_STN)
 
 
+class _StnMultiFn(torch.autograd.Function):
+    """All per-scale stn warps in one launch each way; inputs (frame_0..frame_{n-1}, flow_0..flow_{n-1})."""
+
+    @staticmethod
+    def _scales(frames, flows, outs=None, gouts=None, gflows=None):
+        n = len(flows)
+        arr = (_lib.StnScale * n)()
+        for i in range(n):
+            arr[i].frame, arr[i].flow = frames[i].data_ptr(), flows[i].data_ptr()
+            arr[i].out = outs[i].data_ptr() if outs is not None else None
+            arr[i].g_out = gouts[i].data_ptr() if gouts is not None else None
+            arr[i].g_flow = gflows[i].data_ptr() if gflows is not None else None
+            arr[i].h, arr[i].w = flows[i].shape[2], flows[i].shape[3]
+        return arr
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        n = len(tensors) // 2
+        frames = [_prep(t, "stn frame") for t in tensors[:n]]
+        flows = [_prep(t, "stn flow") for t in tensors[n:]]
+        B, C = frames[0].shape[:2]
+        for fr, fl in zip(frames, flows):
+            if fr.shape[0] != B or fr.shape[1] != C or fl.shape[0] != B or fl.shape[1] != 2 or fr.shape[2:] != fl.shape[2:]:
+                raise ValueError("stn_warp_multi: every frame must be [B,C,h,w] with a [B,2,h,w] flow")
+        outs = [torch.empty_like(fr) for fr in frames]
+        nbytes = sum(4 * B * fl.shape[2] * fl.shape[3] * (2 * C + 2) for fl in flows)
+        with torch.cuda.device(frames[0].device), region(f"stn_multi_fwd n{n} C{C} {flows[0].shape[2]}x{flows[0].shape[3]}",
+                                                         nbytes):
+            arr = _StnMultiFn._scales(frames, flows, outs=outs)
+            _lib.check(_lib.lib().ofr_stn_multi_fwd(arr, n, B, C, _stream()), "ofr_stn_multi_fwd")
+        ctx.save_for_backward(*frames, *flows)
+        ctx.n = n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        n = ctx.n
+        frames, flows = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        B, C = frames[0].shape[:2]
+        if not any(ctx.needs_input_grad[n:]):
+            return (None,) * (2 * n)
+        gouts = [_prep(g if g is not None else torch.zeros_like(fr), "stn grad_output") for g, fr in zip(gouts, frames)]
+        gflows = [torch.empty_like(fl) for fl in flows]
+        nbytes = sum(4 * B * fl.shape[2] * fl.shape[3] * (2 * C + 4) for fl in flows)
+        with torch.cuda.device(frames[0].device), region(f"stn_multi_bwd n{n} C{C} {flows[0].shape[2]}x{flows[0].shape[3]}",
+                                                         nbytes):
+            arr = _StnMultiFn._scales(frames, flows, gouts=gouts, gflows=gflows)
+            _lib.check(_lib.lib().ofr_stn_multi_bwd(arr, n, B, C, _stream()), "ofr_stn_multi_bwd")
+        return (None,) * n + tuple(g if need else None for g, need in zip(gflows, ctx.needs_input_grad[n:]))
+
+
+def stn_warp_multi(flows, frame):
+    """``[stn_warp(flow, frame) for flow in flows]`` -- the per-scale loop of ``opticalFlowReg.forward``
+    (models.py:277-281) -- with one kernel launch for all scales in each direction (most scales are a few thousand
+    pixels: a launch per scale is pure latency).  The frame needs no gradient (it is an input image); a frame that
+    requires one must use ``stn_warp``."""
+    flows = list(flows)
+    if len(flows) > _lib.STN_MAX_SCALES:
+        raise ValueError(f"stn_warp_multi: at most {_lib.STN_MAX_SCALES} scales")
+    if frame.requires_grad:
+        return [stn_warp(fl, frame) for fl in flows]
+    frames = []
+    for fl in flows:
+        h, w = fl.shape[2:]
+        frames.append(frame if frame.shape[2:] == (h, w) else
+                      F.interpolate(frame, size=(h, w), mode="bilinear", align_corners=True))
+    return list(_StnMultiFn.apply(*frames, *flows))
+
+
 def pwc_warp(x, flo, flow_scale=1.0):
     """``PWCDCNet.warp(x, flo)`` (PWC/models/PWCNet.py:143-179) in one pass: sample, build the
     ones-mask, threshold at 0.9999 and multiply, without materialising grid or mask.

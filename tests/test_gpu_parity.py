@@ -288,6 +288,28 @@ def test_pwc_warp_fused_flow_scale(ofr):
     close(res[1][2], res[0][2], atol=1e-6, rtol=1e-6, what="flow gradient through the fused scale")
 
 
+def test_stn_warp_multi_equals_the_per_scale_loop(ofr):
+    """stn_warp_multi(flows, frame) == [stn_warp(f, frame) for f in flows] (models.py:277-281), values and gradients,
+    over a pyramid with ragged and tiny scales."""
+    B = 3
+    frame = torch.rand(B, 1, 40, 36, generator=gen(60)).to(DEV)
+    sizes = [(40, 36), (20, 18), (10, 9), (5, 5), (2, 3)]
+    flows = [(torch.randn(B, 2, h, w, generator=gen(61 + i)) * 2).to(DEV) for i, (h, w) in enumerate(sizes)]
+    gos = [torch.randn(B, 1, h, w, generator=gen(70 + i)).to(DEV) for i, (h, w) in enumerate(sizes)]
+    res = []
+    for multi in (False, True):
+        fl = [f.clone().requires_grad_(True) for f in flows]
+        outs = ofr.stn_warp_multi(fl, frame) if multi else [ofr.stn_warp(f, frame) for f in fl]
+        total = sum((o * g).sum() for o, g in zip(outs, gos))
+        res.append(([o.detach() for o in outs], torch.autograd.grad(total, fl)))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+    ref = oracle.stn_warp(flows[1].cpu().double(), frame.cpu().double())
+    close(res[1][0][1], ref, atol=1e-5, what="stn multi vs oracle")
+
+
 # =============================================================================== loss
 def test_loss_vs_reference_golden(ofr, golden):
     g = golden("loss")
