@@ -406,7 +406,10 @@ __global__ void __launch_bounds__(kTileThreads) resample_prep_kernel(const float
 }
 
 // blockIdx = (target tile x, target tile y, image * csplit + split); launched with cluster dims (1, 1, csplit).
-template <int MODE, bool WANT1, bool WANT2>
+// HW != 0: the plane size Hf*Wf == Hin*Win is this compile-time constant, so the channel offsets of the 16-channel
+// gathers are instruction immediates (with a run-time stride a third of the kernel's issue slots were 64-bit address
+// arithmetic).  Instantiated for the power-of-two maps of the PWC-Net pyramid.
+template <int MODE, bool WANT1, bool WANT2, int HW>
 __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
     const float* __restrict__ in1, const float* __restrict__ gO, const int4* __restrict__ recs,
     const int4* __restrict__ bbox, float* __restrict__ gI1, float* __restrict__ gI2, WarpGeom g, int stx, int sty,
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
     const int tx0 = blockIdx.x * kTX, ty0 = blockIdx.y * kTY;
     const int tx = tx0 + lx, ty = ty0 + ly;
     const bool live = tx < g.Win && ty < g.Hin;
-    const int hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
+    const int hwf = HW ? HW : g.Hf * g.Wf, hwi = HW ? HW : g.Hin * g.Win;
     const int nst = stx * sty;
     const int cxmin = tx0 - 1, cymin = ty0 - 1;  // cell (ky, kx) is binned at [ky - cymin][kx - cxmin]
     const int4* recs_b = recs + (size_t)b * nst * kTileThreads;
@@ -602,10 +605,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                 float gv[kChunk];
                 if (nc == kChunk) {  // full chunk: no per-channel predicates
 #pragma unroll
-                    for (int k = 0; k < kChunk; ++k, gp += hwf) gv[k] = __ldg(gp);
+                    for (int k = 0; k < kChunk; ++k) gv[k] = __ldg(gp + k * hwf);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < kChunk; ++k, gp += hwf) gv[k] = (k < nc) ? __ldg(gp) : 0.f;
+                    for (int k = 0; k < kChunk; ++k) gv[k] = (k < nc) ? __ldg(gp + k * hwf) : 0.f;
                 }
 #pragma unroll
                 for (int k = 0; k < kChunk; ++k) acc[k] = fmaf(w, gv[k], acc[k]);
@@ -642,8 +645,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
             if (live) {
                 float* o = gI1 + ((size_t)b * g.C + c0) * hwi + ty * g.Win + tx;
 #pragma unroll
-                for (int k = 0; k < kChunk; ++k, o += hwi)
-                    if (k < nc) *o = acc[k];
+                for (int k = 0; k < kChunk; ++k)
+                    if (k < nc) o[k * hwi] = acc[k];
             }
         }
         if (WANT2 && live) {
@@ -653,10 +656,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
             const float *pbl = img + max(ot.bl, 0), *pbr = img + max(ot.br, 0);
             const float* pg = go + orem;
 #pragma unroll 4
-            for (int k = 0; k < nc; ++k, ptl += hwi, ptr += hwi, pbl += hwi, pbr += hwi, pg += hwf) {
-                const float gv = __ldg(pg);
-                const float tl = ot.tl >= 0 ? __ldg(ptl) : 0.f, tr = ot.tr >= 0 ? __ldg(ptr) : 0.f;
-                const float bl = ot.bl >= 0 ? __ldg(pbl) : 0.f, br = ot.br >= 0 ? __ldg(pbr) : 0.f;
+            for (int k = 0; k < nc; ++k) {
+                const float gv = __ldg(pg + k * hwf);
+                const float tl = ot.tl >= 0 ? __ldg(ptl + k * hwi) : 0.f, tr = ot.tr >= 0 ? __ldg(ptr + k * hwi) : 0.f;
+                const float bl = ot.bl >= 0 ? __ldg(pbl + k * hwi) : 0.f, br = ot.br >= 0 ? __ldg(pbr + k * hwi) : 0.f;
                 ax = fmaf(gv, fmaf(owy1, br - bl, owy0 * (tr - tl)), ax);
                 ay = fmaf(gv, fmaf(owx1, br - tr, owx0 * (bl - tl)), ay);
             }
@@ -758,7 +761,7 @@ int launch_flow_only(const float* in1, const float* flow, const float* gO, float
     return OFR_OK;
 }
 
-template <int MODE, bool WANT1, bool WANT2>
+template <int MODE, bool WANT1, bool WANT2, int HW = 0>
 int launch_fused(const float* in1, const float* gO, const int4* recs, const int4* bbox, float* gI1, float* gI2,
                  const WarpGeom& g, const WsLayout& L, float sx, float sy, cudaStream_t st) {
     const int ttx = (g.Win + kTX - 1) / kTX, tty = (g.Hin + kTY - 1) / kTY;
@@ -781,7 +784,7 @@ int launch_fused(const float* in1, const float* gO, const int4* recs, const int4
     attr[0].val.clusterDim.z = csplit;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFR_CUDA(cudaLaunchKernelEx(&cfg, resample_bwd_fused_kernel<MODE, WANT1, WANT2>, in1, gO, recs, bbox, gI1, gI2, g,
+    OFR_CUDA(cudaLaunchKernelEx(&cfg, resample_bwd_fused_kernel<MODE, WANT1, WANT2, HW>, in1, gO, recs, bbox, gI1, gI2, g,
                                 L.stx, L.sty, csplit, chunks_per_cta, sx, sy));
     OFR_LAUNCH_CHECK();
     return OFR_OK;
@@ -808,7 +811,19 @@ int run_bwd(const float* in1, const float* flow, const float* gO, float* gI1, fl
     OFR_LAUNCH_CHECK();
     // the flow gradient rides along when source and target grids coincide (always for stn / PWC)
     const bool same = g.Hf == g.Hin && g.Wf == g.Win;
-    if (gI2 && same) return launch_fused<MODE, true, true>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+    if (gI2 && same) {
+        if (MODE == OFR_WARP_PWC) {  // the pyramid levels of PWC-Net: plane size known at compile time
+            switch (g.Hf * g.Wf) {
+                case 128 * 128: return launch_fused<MODE, true, true, 128 * 128>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+                case 64 * 64: return launch_fused<MODE, true, true, 64 * 64>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+                case 32 * 32: return launch_fused<MODE, true, true, 32 * 32>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+                case 16 * 16: return launch_fused<MODE, true, true, 16 * 16>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+                case 8 * 8: return launch_fused<MODE, true, true, 8 * 8>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+                default: break;
+            }
+        }
+        return launch_fused<MODE, true, true>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
+    }
     int rc = launch_fused<MODE, true, false>(in1, gO, recs, bbox, gI1, gI2, g, L, sx, sy, st);
     if (rc == OFR_OK && gI2) rc = launch_flow_only<MODE>(in1, flow, gO, gI2, g, sx, sy, st);
     return rc;
