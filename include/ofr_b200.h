@@ -156,6 +156,12 @@ int ofr_stn_multi_bwd(const ofr_stn_scale_t* scales, int n_scales, int B, int C,
 int ofr_chnorm_fwd(const float* x, float* out, int B, int C, int H, int W, ofr_stream_t stream);
 int ofr_chnorm_bwd(const float* x, const float* out, const float* gO, float* gI,
                    int B, int C, int H, int W, ofr_stream_t stream);
+/* ChannelNorm of a difference, ||x - x2||, without materialising it: the `x[:, :3] - resampled` -> channelnorm pairs of
+ * flownet2/models.py:140-141,152-153,166-167,179-180.  Backward: gI = gradient of x, gI2 = gradient of x2 (= -gI);
+ * either may be NULL. */
+int ofr_chnorm_diff_fwd(const float* x, const float* x2, float* out, int B, int C, int H, int W, ofr_stream_t stream);
+int ofr_chnorm_diff_bwd(const float* x, const float* x2, const float* out, const float* gO, float* gI, float* gI2,
+                        int B, int C, int H, int W, ofr_stream_t stream);
 
 /* ------------------------------------------------------------------ Self-supervised loss
  * Replaces OFEloss and its three terms -- loss.py:9-13 (photometric), :23-35

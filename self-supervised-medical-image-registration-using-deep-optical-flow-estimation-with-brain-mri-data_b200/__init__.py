@@ -9,13 +9,13 @@ reached through the C ABI of ``include/ofr_b200.h``.
 """
 from . import _lib
 from ._lib import build, launch_count, LIB_PATH, EXPORTS
-from .layers import (Correlation, Resample2d, ChannelNorm, stn_warp, stn_warp_multi, pwc_warp, spatial_correlation_sample,
+from .layers import (Correlation, Resample2d, ChannelNorm, stn_warp, stn_warp_multi, pwc_warp, channelnorm_diff, spatial_correlation_sample,
                      correlation_out_shape)
 from .loss import OFEloss, photometric_loss, correlation_loss, smoothness_loss
 from .shims import install as install_shims, uninstall as uninstall_shims
 
 __all__ = [
-    "Correlation", "Resample2d", "ChannelNorm", "stn_warp", "stn_warp_multi", "pwc_warp", "spatial_correlation_sample",
+    "Correlation", "Resample2d", "ChannelNorm", "stn_warp", "stn_warp_multi", "pwc_warp", "channelnorm_diff", "spatial_correlation_sample",
     "correlation_out_shape", "OFEloss", "photometric_loss", "correlation_loss", "smoothness_loss",
     "install_shims", "uninstall_shims", "build", "launch_count", "LIB_PATH", "EXPORTS",
 ]

@@ -94,6 +94,8 @@ def _declare(lib):
         "ofr_stn_multi_bwd": (c_int, [ctypes.POINTER(StnScale), c_int, c_int, c_int, vp]),
         "ofr_chnorm_fwd": (c_int, [vp, vp] + [c_int] * 4 + [vp]),
         "ofr_chnorm_bwd": (c_int, [vp, vp, vp, vp] + [c_int] * 4 + [vp]),
+        "ofr_chnorm_diff_fwd": (c_int, [vp, vp, vp] + [c_int] * 4 + [vp]),
+        "ofr_chnorm_diff_bwd": (c_int, [vp, vp, vp, vp, vp, vp] + [c_int] * 4 + [vp]),
         "ofr_loss_workspace": (c_size_t, [c_int]),
         "ofr_loss_fwd": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(LossScale), c_int, dbl, dbl, dbl,
                                  vp, vp, vp, c_size_t, vp]),
@@ -111,7 +113,7 @@ EXPORTS = ["ofr_abi_version", "ofr_error_string", "ofr_launch_count", "ofr_corr_
            "ofr_corr_fwd", "ofr_corr_fwd_act",
            "ofr_corr_bwd", "ofr_resample_fwd", "ofr_resample_fwd_scaled", "ofr_resample_bwd_workspace", "ofr_resample_bwd",
            "ofr_resample_bwd_scaled", "ofr_stn_multi_fwd", "ofr_stn_multi_bwd",
-           "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd"]
+           "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_chnorm_diff_fwd", "ofr_chnorm_diff_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd"]
 
 
 def lib():

@@ -24,6 +24,8 @@ struct Pix<4> {
     }
     static __device__ __forceinline__ T sqrt(T a) { return make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w)); }
     static __device__ __forceinline__ T mul(T a, T b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+    static __device__ __forceinline__ T sub(T a, T b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+    static __device__ __forceinline__ T neg(T a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
     static __device__ __forceinline__ T ratio(T g, T o) {
         return make_float4(g.x / (o.x + 1e-8f), g.y / (o.y + 1e-8f), g.z / (o.z + 1e-8f), g.w / (o.w + 1e-8f));
     }
@@ -37,6 +39,8 @@ struct Pix<1> {
     static __device__ __forceinline__ T fma(T a, T b, T c) { return fmaf(a, b, c); }
     static __device__ __forceinline__ T sqrt(T a) { return sqrtf(a); }
     static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __device__ __forceinline__ T neg(T a) { return -a; }
     static __device__ __forceinline__ T ratio(T g, T o) { return g / (o + 1e-8f); }
 };
 
@@ -45,9 +49,12 @@ constexpr int kVPT = 4;  // vectors per thread: their loads are all issued befor
 
 // thread -> vectors (blockIdx.x * kVPT + j) * kThreads + threadIdx.x, j < kVPT: every load / store of a warp is one
 // contiguous 512-byte run
+// x2 != nullptr: the norm of the difference x - x2 (`x1 - resample(...)` then ChannelNorm at flownet2/models.py:140-141,
+// 152-153, 166-167, 179-180) without materialising the difference
 template <int VEC>
-__global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                              int C, long long hw, long long total_vec) {
+__global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                              float* __restrict__ out, int C, long long hw,
+                                                              long long total_vec) {
     const long long hwv = hw / VEC;
     const long long i0 = (long long)blockIdx.x * kVPT * kThreads + threadIdx.x;
     const float* xp[kVPT];
@@ -62,6 +69,7 @@ __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __res
         xp[j] = x + b * C * hw + p;
         op[j] = out + b * hw + p;
     }
+    const long long d2 = x2 ? x2 - x : 0;  // element distance between the two inputs
     typename Pix<VEC>::T s[kVPT];
 #pragma unroll
     for (int j = 0; j < kVPT; ++j) s[j] = Pix<VEC>::zero();
@@ -69,6 +77,11 @@ __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __res
         typename Pix<VEC>::T v[kVPT];
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
+        if (x2) {
+#pragma unroll
+            for (int j = 0; j < kVPT; ++j)
+                if (ok[j]) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xp[j] + d2));
+        }
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) {
             s[j] = Pix<VEC>::fma(v[j], v[j], s[j]);
@@ -80,10 +93,13 @@ __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __res
         if (ok[j]) Pix<VEC>::st(op[j], Pix<VEC>::sqrt(s[j]));
 }
 
+// x2 != nullptr: backward of the norm of x - x2; gI gets the gradient of x, gI2 (optional) its negative for x2
 template <int VEC>
-__global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ out,
+__global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x2,
+                                                              const float* __restrict__ out,
                                                               const float* __restrict__ gO, float* __restrict__ gI,
-                                                              int C, long long hw, long long total_vec) {
+                                                              float* __restrict__ gI2, int C, long long hw,
+                                                              long long total_vec) {
     const long long hwv = hw / VEC;
     const long long i0 = (long long)blockIdx.x * kVPT * kThreads + threadIdx.x;
     const float* xp[kVPT];
@@ -97,18 +113,26 @@ __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __res
         const long long ic = ok[j] ? i : 0;
         const long long b = ic / hwv, p = (ic - b * hwv) * VEC;
         xp[j] = x + b * C * hw + p;
-        gp[j] = gI + b * C * hw + p;
+        gp[j] = gI ? gI + b * C * hw + p : nullptr;
         r[j] = Pix<VEC>::ratio(Pix<VEC>::ld(gO + b * hw + p), Pix<VEC>::ld(out + b * hw + p));
     }
+    const long long d2 = x2 ? x2 - x : 0, dg = (gI && gI2) ? gI2 - gI : 0;
     for (int c = 0; c < C; ++c) {
         typename Pix<VEC>::T v[kVPT];
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
+        if (x2) {
+#pragma unroll
+            for (int j = 0; j < kVPT; ++j)
+                if (ok[j]) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xp[j] + d2));
+        }
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) {
-            if (ok[j]) Pix<VEC>::st(gp[j], Pix<VEC>::mul(v[j], r[j]));
+            const typename Pix<VEC>::T gq = Pix<VEC>::mul(v[j], r[j]);
+            if (ok[j] && gI) Pix<VEC>::st(gp[j], gq);
+            if (ok[j] && gI2) Pix<VEC>::st(gI ? gp[j] + dg : gI2 + (xp[j] - x), Pix<VEC>::neg(gq));
             xp[j] += hw;
-            gp[j] += hw;
+            if (gI) gp[j] += hw;
         }
     }
 }
@@ -116,15 +140,20 @@ __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __res
 }  // namespace
 
 extern "C" int ofr_chnorm_fwd(const float* x, float* out, int B, int C, int H, int W, ofr_stream_t stream) {
+    return ofr_chnorm_diff_fwd(x, nullptr, out, B, C, H, W, stream);
+}
+
+extern "C" int ofr_chnorm_diff_fwd(const float* x, const float* x2, float* out, int B, int C, int H, int W,
+                                   ofr_stream_t stream) {
     if (!x || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return OFR_EINVAL;
     const long long hw = (long long)H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out)) {
+    if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && (!x2 || ofr::aligned16(x2))) {
         const long long n = (long long)B * hw / 4;
-        chnorm_fwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, C, hw, n);
+        chnorm_fwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_fwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, C, hw, n);
+        chnorm_fwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;
@@ -132,15 +161,23 @@ extern "C" int ofr_chnorm_fwd(const float* x, float* out, int B, int C, int H, i
 
 extern "C" int ofr_chnorm_bwd(const float* x, const float* out, const float* gO, float* gI, int B, int C, int H,
                               int W, ofr_stream_t stream) {
-    if (!x || !out || !gO || !gI || B <= 0 || C <= 0 || H <= 0 || W <= 0) return OFR_EINVAL;
+    if (!gI) return OFR_EINVAL;
+    return ofr_chnorm_diff_bwd(x, nullptr, out, gO, gI, nullptr, B, C, H, W, stream);
+}
+
+extern "C" int ofr_chnorm_diff_bwd(const float* x, const float* x2, const float* out, const float* gO, float* gI,
+                                   float* gI2, int B, int C, int H, int W, ofr_stream_t stream) {
+    if (!x || !out || !gO || (!gI && !gI2) || (gI2 && !x2) || B <= 0 || C <= 0 || H <= 0 || W <= 0) return OFR_EINVAL;
     const long long hw = (long long)H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && ofr::aligned16(gO) && ofr::aligned16(gI)) {
+    const bool al = ofr::aligned16(x) && ofr::aligned16(out) && ofr::aligned16(gO) && (!gI || ofr::aligned16(gI)) &&
+                    (!gI2 || ofr::aligned16(gI2)) && (!x2 || ofr::aligned16(x2));
+    if (hw % 4 == 0 && al) {
         const long long n = (long long)B * hw / 4;
-        chnorm_bwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
+        chnorm_bwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_bwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, out, gO, gI, C, hw, n);
+        chnorm_bwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;

@@ -325,6 +325,42 @@ class _ChannelNormFn(torch.autograd.Function):
         return g
 
 
+class _ChannelNormDiffFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _prep(a, "ChannelNorm input1"), _prep(b, "ChannelNorm input2")
+        if a.shape != b.shape:
+            raise ValueError(f"channelnorm_diff: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+        B, C, H, W = a.shape
+        out = torch.empty(B, 1, H, W, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device), region(f"chnorm_diff_fwd C{C} {H}x{W}", 4 * B * H * W * (2 * C + 1)):
+            _lib.check(_lib.lib().ofr_chnorm_diff_fwd(_ptr(a), _ptr(b), _ptr(out), B, C, H, W, _stream()),
+                       "ofr_chnorm_diff_fwd")
+        ctx.save_for_backward(a, b, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, b, out = ctx.saved_tensors
+        B, C, H, W = a.shape
+        grad_out = _prep(grad_out, "ChannelNorm grad_output")
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        if ga is None and gb is None:
+            return None, None
+        n_out = (ga is not None) + (gb is not None)
+        with torch.cuda.device(a.device), region(f"chnorm_diff_bwd C{C} {H}x{W}", 4 * B * H * W * ((2 + n_out) * C + 2)):
+            _lib.check(_lib.lib().ofr_chnorm_diff_bwd(_ptr(a), _ptr(b), _ptr(out), _ptr(grad_out), _ptr(ga), _ptr(gb),
+                                                      B, C, H, W, _stream()), "ofr_chnorm_diff_bwd")
+        return ga, gb
+
+
+def channelnorm_diff(a, b):
+    """``ChannelNorm()(a - b)`` in one pass (the ``x[:, :3] - resampled`` -> ``channelnorm`` pairs of
+    flownet2/models.py:140-141,152-153,166-167,179-180) without materialising the difference."""
+    return _ChannelNormDiffFn.apply(a, b)
+
+
 class ChannelNorm(nn.Module):
     """Per-pixel L2 norm over channels (flownet2 ``ChannelNorm``; ``norm_deg`` is ignored upstream too)."""
 

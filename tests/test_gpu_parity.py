@@ -288,6 +288,23 @@ def test_pwc_warp_fused_flow_scale(ofr):
     close(res[1][2], res[0][2], atol=1e-6, rtol=1e-6, what="flow gradient through the fused scale")
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 1, 7, 9), (2, 2, 33, 5)])
+def test_channelnorm_diff_equals_channelnorm_of_the_difference(ofr, shape):
+    """channelnorm_diff(a, b) == ChannelNorm()(a - b) (flownet2/models.py:140-141), values and both gradients."""
+    a0 = torch.randn(*shape, generator=gen(90)).to(DEV)
+    b0 = torch.randn(*shape, generator=gen(91)).to(DEV)
+    b0[0, :, 0, 0] = a0[0, :, 0, 0]  # a zero difference: the 1e-8 guard of the backward
+    go = torch.randn(shape[0], 1, *shape[2:], generator=gen(92)).to(DEV)
+    res = []
+    for fused in (False, True):
+        a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        out = ofr.channelnorm_diff(a, b) if fused else ofr.ChannelNorm()(a - b)
+        res.append((out.detach(),) + torch.autograd.grad(out, (a, b), go))
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)
+    assert torch.isfinite(res[1][1]).all()
+
+
 def test_stn_warp_multi_equals_the_per_scale_loop(ofr):
     """stn_warp_multi(flows, frame) == [stn_warp(f, frame) for f in flows] (models.py:277-281), values and gradients,
     over a pyramid with ragged and tiny scales."""
