@@ -51,7 +51,7 @@ constexpr int kVPT = 4;  // vectors per thread: their loads are all issued befor
 // contiguous 512-byte run
 // x2 != nullptr: the norm of the difference x - x2 (`x1 - resample(...)` then ChannelNorm at flownet2/models.py:140-141,
 // 152-153, 166-167, 179-180) without materialising the difference
-template <int VEC>
+template <int VEC, bool DIFF>
 __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                               float* __restrict__ out, int C, long long hw,
                                                               long long total_vec) {
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __res
         xp[j] = x + b * C * hw + p;
         op[j] = out + b * hw + p;
     }
-    const long long d2 = x2 ? x2 - x : 0;  // element distance between the two inputs
+    const long long d2 = DIFF ? x2 - x : 0;  // element distance between the two inputs
     typename Pix<VEC>::T s[kVPT];
 #pragma unroll
     for (int j = 0; j < kVPT; ++j) s[j] = Pix<VEC>::zero();
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __res
         typename Pix<VEC>::T v[kVPT];
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
-        if (x2) {
+        if (DIFF) {
 #pragma unroll
             for (int j = 0; j < kVPT; ++j)
                 if (ok[j]) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xp[j] + d2));
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __res
 }
 
 // x2 != nullptr: backward of the norm of x - x2; gI gets the gradient of x, gI2 (optional) its negative for x2
-template <int VEC>
+template <int VEC, bool DIFF>
 __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                               const float* __restrict__ out,
                                                               const float* __restrict__ gO, float* __restrict__ gI,
@@ -113,15 +113,15 @@ __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __res
         const long long ic = ok[j] ? i : 0;
         const long long b = ic / hwv, p = (ic - b * hwv) * VEC;
         xp[j] = x + b * C * hw + p;
-        gp[j] = gI ? gI + b * C * hw + p : nullptr;
+        gp[j] = (DIFF && !gI) ? gI2 + b * C * hw + p : gI + b * C * hw + p;  // DIFF: gI and / or gI2
         r[j] = Pix<VEC>::ratio(Pix<VEC>::ld(gO + b * hw + p), Pix<VEC>::ld(out + b * hw + p));
     }
-    const long long d2 = x2 ? x2 - x : 0, dg = (gI && gI2) ? gI2 - gI : 0;
+    const long long d2 = DIFF ? x2 - x : 0, dg = (DIFF && gI && gI2) ? gI2 - gI : 0;
     for (int c = 0; c < C; ++c) {
         typename Pix<VEC>::T v[kVPT];
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
-        if (x2) {
+        if (DIFF) {
 #pragma unroll
             for (int j = 0; j < kVPT; ++j)
                 if (ok[j]) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xp[j] + d2));
@@ -129,10 +129,14 @@ __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __res
 #pragma unroll
         for (int j = 0; j < kVPT; ++j) {
             const typename Pix<VEC>::T gq = Pix<VEC>::mul(v[j], r[j]);
-            if (ok[j] && gI) Pix<VEC>::st(gp[j], gq);
-            if (ok[j] && gI2) Pix<VEC>::st(gI ? gp[j] + dg : gI2 + (xp[j] - x), Pix<VEC>::neg(gq));
+            if (!DIFF) {
+                if (ok[j]) Pix<VEC>::st(gp[j], gq);
+            } else if (ok[j]) {
+                if (gI) Pix<VEC>::st(gp[j], gq);
+                if (gI2) Pix<VEC>::st(gI ? gp[j] + dg : gp[j], Pix<VEC>::neg(gq));
+            }
             xp[j] += hw;
-            if (gI) gp[j] += hw;
+            gp[j] += hw;
         }
     }
 }
@@ -150,10 +154,12 @@ extern "C" int ofr_chnorm_diff_fwd(const float* x, const float* x2, float* out, 
     cudaStream_t st = (cudaStream_t)stream;
     if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && (!x2 || ofr::aligned16(x2))) {
         const long long n = (long long)B * hw / 4;
-        chnorm_fwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
+        if (x2) chnorm_fwd_kernel<4, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
+        else chnorm_fwd_kernel<4, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_fwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
+        if (x2) chnorm_fwd_kernel<1, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
+        else chnorm_fwd_kernel<1, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;
@@ -174,10 +180,12 @@ extern "C" int ofr_chnorm_diff_bwd(const float* x, const float* x2, const float*
                     (!gI2 || ofr::aligned16(gI2)) && (!x2 || ofr::aligned16(x2));
     if (hw % 4 == 0 && al) {
         const long long n = (long long)B * hw / 4;
-        chnorm_bwd_kernel<4><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
+        if (x2) chnorm_bwd_kernel<4, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
+        else chnorm_bwd_kernel<4, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
     } else {
         const long long n = (long long)B * hw;
-        chnorm_bwd_kernel<1><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
+        if (x2) chnorm_bwd_kernel<1, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
+        else chnorm_bwd_kernel<1, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
     }
     OFR_LAUNCH_CHECK();
     return OFR_OK;
