@@ -788,9 +788,14 @@ int launch_fused(const float* in1, const float* gO, const int4* recs, const int4
     const int nchunks = (g.C + kChunk - 1) / kChunk;
     // split the channel chunks over a cluster only as far as needed to give every SM a few CTAs
     const long long ntile = (long long)ttx * tty * g.B;
+    // (a divisor of the chunk count, so no rank of the cluster idles: 6 chunks at 32x32 split 6 ways, not 4)
     int csplit = 1;
-    while (csplit < kMaxSplit && csplit * 2 <= nchunks && ntile * csplit < 3ll * ofr::sm_count()) csplit *= 2;
-    const int chunks_per_cta = (nchunks + csplit - 1) / csplit;
+    for (int cs = 1; cs <= kMaxSplit && cs <= nchunks; ++cs) {
+        if (nchunks % cs) continue;
+        csplit = cs;
+        if (ntile * cs >= 3ll * ofr::sm_count()) break;
+    }
+    const int chunks_per_cta = nchunks / csplit;
     if ((long long)g.B * csplit > 65535 || tty > 65535) return OFR_ENOTSUP;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ttx, tty, g.B * csplit);
