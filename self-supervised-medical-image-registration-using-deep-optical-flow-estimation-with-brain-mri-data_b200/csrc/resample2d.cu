@@ -455,9 +455,18 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
             }
             if (hit) tlist[pre + __popc(m & ((1u << lane) - 1u))] = i;
             __syncthreads();
-            for (int j = 0; j < tot; ++j) {
-                const int t = tlist[j];
-                body(t, __ldg(recs_b + (size_t)t * kTileThreads + tid));
+            // four tiles' records in flight at once: the loop is a chain of L2 round trips otherwise
+            for (int j = 0; j < tot; j += 4) {
+                int t[4];
+                int4 r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    t[k] = tlist[min(j + k, tot - 1)];
+                    r[k] = __ldg(recs_b + (size_t)t[k] * kTileThreads + tid);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (j + k < tot) body(t[k], r[k]);
             }
             __syncthreads();
         }
