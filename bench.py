@@ -96,7 +96,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ model builders
-def build_gpu_step(device, channels_last=False):
+def build_gpu_step(device, channels_last=False, fused_loss=True):
     import ofr_b200 as ofr
     from ofr_b200.harness import PWCNetHost, RegistrationStep
     torch.manual_seed(6)
@@ -104,7 +104,10 @@ def build_gpu_step(device, channels_last=False):
     if channels_last:  # host-model memory format only; the ofr_b200 layers take / return NCHW (they call .contiguous())
         host = host.to(memory_format=torch.channels_last)
     host.deconv0.requires_grad_(False)  # unused in the forward (PWCNet.py:126,274): keep it out of DDP's reducer
-    return RegistrationStep(host, ofr.stn_warp, ofr.OFEloss, stn_multi=ofr.stn_warp_multi), ofr
+    # fused_loss: the stn warps of all scales + OFEloss as one launch each way (ofr_regloss_fwd/bwd, bit-identical to
+    # stn_warp_multi + OFEloss)
+    return RegistrationStep(host, ofr.stn_warp, ofr.OFEloss, stn_multi=ofr.stn_warp_multi,
+                            reg_loss=ofr.registration_loss if fused_loss else None), ofr
 
 
 def build_cpu_step():
@@ -179,7 +182,7 @@ def run_ours(args):
     from ofr_b200.profiling import KernelTimer
 
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
-    step, ofr = build_gpu_step(device, channels_last=args.channels_last)
+    step, ofr = build_gpu_step(device, channels_last=args.channels_last, fused_loss=bool(args.fused_loss))
     if world > 1:
         step.predictor = torch.nn.parallel.DistributedDataParallel(step.predictor, device_ids=[local],
                                                                    gradient_as_bucket_view=True)
@@ -268,6 +271,7 @@ def run_ours(args):
                        "optimizer": "Adam(lr=1e-4, eps=1e-4)", "parallelism": f"dp{world}",
                        "host_memory_format": "channels_last" if args.channels_last else "contiguous (NCHW)",
                        "cudnn_benchmark": bool(args.cudnn_benchmark),
+                       "loss": "fused stn + OFEloss (ofr_regloss_fwd/bwd)" if args.fused_loss else "stn_multi then OFEloss",
                        "l2": "working set (activations > 1 GB per step) exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "kernels": rows[:24], "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_host.numel() * 4 * world,
@@ -290,6 +294,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: pairs per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--channels-last", type=int, default=0, help="host model (cuDNN convolutions) in channels_last")
+    ap.add_argument("--fused-loss", type=int, default=1,
+                    help="1: stn warps + OFEloss as the fused registration_loss; 0: stn_warp_multi then OFEloss")
     ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the host model")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -193,6 +193,31 @@ int ofr_loss_bwd(const float* fixed, int B, int Hs, int Ws,
                  double lamb_da, double gamma, double zeta,
                  const double* grad4, const double* state, ofr_stream_t stream);
 
+/* Fused registration loss: the `[self.stn(flow, moving) for flow in flow_predictions]` of
+ * opticalFlowReg.forward (models.py:277) followed by OFEloss (train.py:56 -> loss.py:66-84) in ONE pass per
+ * direction.  `moving` is the moving image already resized to the scale (the F.interpolate of models.py:258 stays
+ * with the caller).  Forward writes the warped image of every scale to `warped` (the model returns them,
+ * models.py:289; the backward reads them back) and the four loss values to out4; backward writes
+ * d total / d flow = smoothness gradient + photometric/NCC gradients chained through the warp to `g_flow` -- the
+ * gradient of the warped images is never materialised.  Bit-identical to ofr_stn_multi_fwd + ofr_loss_fwd and to
+ * ofr_loss_bwd + ofr_stn_multi_bwd + the float32 add autograd performs.  Workspace: ofr_loss_workspace. */
+typedef struct {
+    const float* moving; /* [B,1,h,w]                                     */
+    const float* flow;   /* [B,2,h,w]                                     */
+    float* warped;       /* [B,1,h,w]  written by fwd, read by bwd        */
+    float* g_flow;       /* backward only: [B,2,h,w]                      */
+    int h, w;
+} ofr_regloss_scale_t;
+int ofr_regloss_fwd(const float* fixed, int B, int Hs, int Ws,
+                    const ofr_regloss_scale_t* scales, int n_scales,
+                    double lamb_da, double gamma, double zeta,
+                    double* out4, double* state,
+                    void* ws, size_t ws_bytes, ofr_stream_t stream);
+int ofr_regloss_bwd(const float* fixed, int B, int Hs, int Ws,
+                    const ofr_regloss_scale_t* scales, int n_scales,
+                    double lamb_da, double gamma, double zeta,
+                    const double* grad4, const double* state, ofr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

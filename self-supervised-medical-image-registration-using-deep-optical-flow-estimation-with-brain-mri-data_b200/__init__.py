@@ -11,11 +11,11 @@ from . import _lib
 from ._lib import build, launch_count, LIB_PATH, EXPORTS
 from .layers import (Correlation, Resample2d, ChannelNorm, stn_warp, stn_warp_multi, pwc_warp, channelnorm_diff, spatial_correlation_sample,
                      correlation_out_shape)
-from .loss import OFEloss, photometric_loss, correlation_loss, smoothness_loss
+from .loss import OFEloss, registration_loss, photometric_loss, correlation_loss, smoothness_loss
 from .shims import install as install_shims, uninstall as uninstall_shims
 
 __all__ = [
     "Correlation", "Resample2d", "ChannelNorm", "stn_warp", "stn_warp_multi", "pwc_warp", "channelnorm_diff", "spatial_correlation_sample",
-    "correlation_out_shape", "OFEloss", "photometric_loss", "correlation_loss", "smoothness_loss",
+    "correlation_out_shape", "OFEloss", "registration_loss", "photometric_loss", "correlation_loss", "smoothness_loss",
     "install_shims", "uninstall_shims", "build", "launch_count", "LIB_PATH", "EXPORTS",
 ]

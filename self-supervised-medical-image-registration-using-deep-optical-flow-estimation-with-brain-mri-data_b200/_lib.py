@@ -42,6 +42,12 @@ class StnScale(ctypes.Structure):
 STN_MAX_SCALES = 8
 
 
+class RegLossScale(ctypes.Structure):
+    """Mirror of ``ofr_regloss_scale_t``."""
+    _fields_ = [("moving", ctypes.c_void_p), ("flow", ctypes.c_void_p), ("warped", ctypes.c_void_p),
+                ("g_flow", ctypes.c_void_p), ("h", ctypes.c_int), ("w", ctypes.c_int)]
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -101,6 +107,10 @@ def _declare(lib):
                                  vp, vp, vp, c_size_t, vp]),
         "ofr_loss_bwd": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(LossScale), c_int, dbl, dbl, dbl,
                                  vp, vp, vp]),
+        "ofr_regloss_fwd": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(RegLossScale), c_int, dbl, dbl, dbl,
+                                    vp, vp, vp, c_size_t, vp]),
+        "ofr_regloss_bwd": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(RegLossScale), c_int, dbl, dbl, dbl,
+                                    vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == the library does not export a declared symbol
@@ -113,7 +123,8 @@ EXPORTS = ["ofr_abi_version", "ofr_error_string", "ofr_launch_count", "ofr_corr_
            "ofr_corr_fwd", "ofr_corr_fwd_act",
            "ofr_corr_bwd", "ofr_resample_fwd", "ofr_resample_fwd_scaled", "ofr_resample_bwd_workspace", "ofr_resample_bwd",
            "ofr_resample_bwd_scaled", "ofr_stn_multi_fwd", "ofr_stn_multi_bwd",
-           "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_chnorm_diff_fwd", "ofr_chnorm_diff_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd"]
+           "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_chnorm_diff_fwd", "ofr_chnorm_diff_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd",
+           "ofr_regloss_fwd", "ofr_regloss_bwd"]
 
 
 def lib():

@@ -22,6 +22,7 @@
 //            d/d warped gets the photometric and NCC terms, d/d flow the smoothness term; `fixed`
 //            is an input image and receives no gradient (it never requires one in the reference).
 #include "ofr_common.cuh"
+#include "warp_math.cuh"
 
 namespace {
 
@@ -43,6 +44,11 @@ struct ScaleDev {
     int rows_per_cta;  // work item = (image, strip of rows_per_cta rows)
     int strips;        // strips per image
     int tx_shift;      // the CTA's 256 threads are (1 << tx_shift) pixel-group columns x (256 >> tx_shift) row lanes
+    // fused registration loss (ofr_regloss_*): warped = stn(flow, moving) is formed inside the kernels
+    const float* moving;     // [B,1,h,w] moving image resized to this scale, or nullptr (plain OFEloss)
+    float* warped_out;       // forward: the warped image is also written here (the backward reads it back)
+    ofr_warp::WarpGeom wg;   // stn geometry of the scale
+    float sx, sy;            // chain factors d(sample position)/d(flow) of the stn grid
 };
 
 struct LossParams {
@@ -71,7 +77,9 @@ __device__ __forceinline__ float charb(float x) { return sqrt_approx(sqrt_approx
 __device__ __forceinline__ float charb_grad(float x) {
     const float s = fmaf(x, x, 1e-18f);
     const float r = rsqrt_approx(s);          // s^-0.5
-    return 0.5f * x * r * sqrt_approx(r);     // s^-0.5 * s^-0.25
+    // (explicitly rounded product: the sums it enters must not contract it into an FMA differently from kernel to
+    // kernel -- the fused registration loss is bit-identical to the separate warp and loss kernels)
+    return __fmul_rn(0.5f * x * r, sqrt_approx(r));  // s^-0.5 * s^-0.25
 }
 
 // F.interpolate(fixed, (h,w), mode='bilinear', align_corners=False) evaluated at one output pixel,
@@ -145,6 +153,14 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
     }
 }
 template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
+    if (VEC == 4)
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
+    else
+        p[0] = v[0];
+}
+
+template <int VEC>
 __device__ __forceinline__ void zero_vec(float (&v)[VEC]) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) v[k] = 0.f;
@@ -181,7 +197,16 @@ __device__ __forceinline__ void fixed_row(const float* __restrict__ fixed, int W
     }
 }
 
-template <int VEC>
+// value of stn(flow, moving) at one pixel: the operation order of resample2d.cu's stn forward (bit-identical)
+__device__ __forceinline__ float stn_value(const float* __restrict__ mv, int x, int y, float u, float v,
+                                           const ofr_warp::WarpGeom& wg) {
+    using namespace ofr_warp;
+    const Samp s = make_samp<OFR_WARP_STN>(x, y, u, v, wg);
+    const float a = tap_sum(mv, fwd_taps<OFR_WARP_STN>(s, wg.Hin, wg.Win));
+    return a;
+}
+
+template <int VEC, bool FUSED>
 __device__ __forceinline__ void partial_body(const LossParams& p, const Strip& st, float (&mm)[4], double (&acc)[7]) {
     const ScaleDev sc = p.sc[st.s];
     const int h = sc.h, w = sc.w, gw = w / VEC, hw = h * w;
@@ -205,7 +230,14 @@ __device__ __forceinline__ void partial_body(const LossParams& p, const Strip& s
         load_vec<VEC>(fvp + o, v);
         for (int y = wk.ya; y < wk.yb; ++y, o += w) {
             float wv[VEC], fx[VEC], ud[VEC], vd[VEC];
-            load_vec<VEC>(wp + o, wv);
+            if (FUSED) {
+                const float* mv = sc.moving + (size_t)st.b * hw;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) wv[k] = stn_value(mv, x + k, y, u[k], v[k], sc.wg);
+                store_vec<VEC>(sc.warped_out + (size_t)st.b * hw + o, wv);
+            } else {
+                load_vec<VEC>(wp + o, wv);
+            }
             if (y + 1 < h) {
                 load_vec<VEC>(fu + o + w, ud);
                 load_vec<VEC>(fvp + o + w, vd);
@@ -243,8 +275,9 @@ __device__ __forceinline__ void partial_body(const LossParams& p, const Strip& s
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) loss_partial_kernel(const __grid_constant__ LossParams p,
-                                                                double* __restrict__ partials) {
+template <bool FUSED>
+__global__ void __launch_bounds__(kThreads, FUSED ? 3 : 4) loss_partial_kernel(const __grid_constant__ LossParams p,
+                                                                            double* __restrict__ partials) {
     __shared__ double red[kNumPart][kThreads / 32];
     const Strip st = strip_of_cta(p);
     double acc[7];
@@ -252,9 +285,9 @@ __global__ void __launch_bounds__(kThreads, 4) loss_partial_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k] = 0.0;
     if (p.sc[st.s].w % 4 == 0)
-        partial_body<4>(p, st, mm, acc);
+        partial_body<4, FUSED>(p, st, mm, acc);
     else
-        partial_body<1>(p, st, mm, acc);
+        partial_body<1, FUSED>(p, st, mm, acc);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const double v = warp_sum(acc[k]);
@@ -369,14 +402,6 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(const __grid_constant_
 }
 
 template <int VEC>
-__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
-    if (VEC == 4)
-        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
-    else
-        p[0] = v[0];
-}
-
-template <int VEC>
 __device__ __forceinline__ void bwd_body(const LossParams& p, const Strip& st, float cp, float cs, float k1, float k2,
                                          float mf, float mw) {
     const ScaleDev sc = p.sc[st.s];
@@ -450,26 +475,149 @@ __device__ __forceinline__ void bwd_body(const LossParams& p, const Strip& st, f
     }
 }
 
-__global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const __grid_constant__ LossParams p,
-                                                            const double* __restrict__ grad4,
-                                                            const double* __restrict__ state) {
-    const Strip st = strip_of_cta(p);
+// Backward of the fused registration loss: d total / d flow = smoothness part + (d total / d warped) chained through
+// stn(flow, moving).  Per thread: the gradient w.r.t. the warped pixels of its rows is formed first (as in bwd_body)
+// and turned into the two flow-gradient contributions of the warp (the arithmetic of resample2d.cu's stn backward,
+// kept in registers), then the smoothness sweeps add theirs: the flow gradient is written once, and neither the
+// gradient of the warped image nor the two partial flow gradients exist in memory.
+template <int VEC>
+__device__ __forceinline__ void bwd_body_fused(const LossParams& p, const Strip& st, float cp, float cs, float k1,
+                                               float k2, float mf, float mw) {
+    using namespace ofr_warp;
+    const ScaleDev sc = p.sc[st.s];
+    const int h = sc.h, w = sc.w, gw = w / VEC, hw = h * w;
+    const float sh = (float)p.Hs / (float)h, sw = (float)p.Ws / (float)w;
+    const bool ident = VEC == 4 && h == p.Hs && w == p.Ws && (p.Ws % 4) == 0 && (reinterpret_cast<uintptr_t>(p.fixed) & 15u) == 0;
+    const float* fixed = p.fixed + (size_t)st.b * p.Hs * p.Ws;
+    const float* wp = sc.warped + (size_t)st.b * hw;
+    const float* mv = sc.moving + (size_t)st.b * hw;
+    const float* f0 = sc.flow + (size_t)st.b * 2 * hw;
+    float* gfp = sc.g_flow + (size_t)st.b * 2 * hw;
+    const Walk wk = walk_of_thread(sc, st);
+    if (wk.ya >= wk.yb) return;
+    for (int g = wk.gx; g < gw; g += wk.tx_n) {
+        const int x = g * VEC;
+        AxisTap tx[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) tx[k] = axis_tap(sw, x + k, p.Ws);
+        float gwarp[2][kRPT][VEC];  // flow-gradient contributions through the warp, rows ya .. ya+kRPT-1
+#pragma unroll
+        for (int r = 0; r < kRPT; ++r) {
+            const int y = wk.ya + r;
+            if (y < wk.yb) {
+                const int o = y * w + x;
+                float wv[VEC], fx[VEC], u[VEC], v[VEC];
+                load_vec<VEC>(wp + o, wv);
+                load_vec<VEC>(f0 + o, u);
+                load_vec<VEC>(f0 + hw + o, v);
+                fixed_row<VEC>(fixed, p.Ws, ident, x, y, axis_tap(sh, y, p.Hs), tx, fx);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    // d total / d warped: photometric -cp * psi(f - w);  NCC k1 * (f - mean f) - k2 * (w - mean w)
+                    const float go = fmaf(-cp, charb_grad(__fsub_rn(fx[k], wv[k])), fmaf(k1, fx[k] - mf, -k2 * (wv[k] - mw)));
+                    const Samp s = make_samp<OFR_WARP_STN>(x + k, y, u[k], v[k], sc.wg);
+                    const TapOff t = tap_offsets<OFR_WARP_STN>(s.x0, s.y0, h, w);
+                    const float tl = fetch(mv, t.tl), tr = fetch(mv, t.tr), bl = fetch(mv, t.bl), br = fetch(mv, t.br);
+                    // d out / d ix = wy0*(TR-TL) + wy1*(BR-BL);  d out / d iy = wx0*(BL-TL) + wx1*(BR-TR)
+                    const float ax = fmaf(go, fmaf(s.wy1, br - bl, s.wy0 * (tr - tl)), 0.f);
+                    const float ay = fmaf(go, fmaf(s.wx1, br - tr, s.wx0 * (bl - tl)), 0.f);
+                    gwarp[0][r][k] = __fmul_rn(ax, sc.sx);
+                    gwarp[1][r][k] = __fmul_rn(ay, sc.sy);
+                }
+            }
+        }
+        const bool has_right = x + VEC < w, has_left = x > 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float* f = f0 + c * hw;
+            float* gp = gfp + c * hw;
+            float v[VEC], up[VEC];  // up[k] = psi(v[y-1][k] - v[y][k]), carried from the previous row
+            {
+                const int o = wk.ya * w + x;
+                load_vec<VEC>(f + o, v);
+                if (wk.ya > 0) {
+                    float t[VEC];
+                    load_vec<VEC>(f + o - w, t);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) up[k] = charb_grad(__fsub_rn(t[k], v[k]));
+                } else {
+                    zero_vec<VEC>(up);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kRPT; ++r) {
+                const int y = wk.ya + r;
+                if (y < wk.yb) {
+                    const int o = y * w + x;
+                    float dn[VEC], gq[VEC], hd[VEC + 1];
+                    if (y + 1 < h) {
+                        load_vec<VEC>(f + o + w, dn);
+                    } else {
+                        zero_vec<VEC>(dn);
+                    }
+                    const float rt = has_right ? __ldg(f + o + VEC) : 0.f;
+                    hd[0] = has_left ? charb_grad(__fsub_rn(__ldg(f + o - 1), v[0])) : 0.f;
+#pragma unroll
+                    for (int k = 1; k <= VEC; ++k)
+                        hd[k] = charb_grad(__fsub_rn(v[k - 1], (k < VEC) ? v[k % VEC] : rt));
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        const float vd = charb_grad(__fsub_rn(v[k], dn[k]));
+                        // autograd adds the two flow gradients as float32 tensors: product, then one rounded add
+                        gq[k] = __fadd_rn(__fmul_rn(cs, ((vd + hd[k + 1]) - up[k]) - hd[k]), gwarp[c][r][k]);
+                        up[k] = vd;
+                        v[k] = dn[k];
+                    }
+                    store_vec<VEC>(gp + o, gq);
+                }
+            }
+        }
+    }
+}
+
+// per-scale coefficients of the backward: upstream gradients x loss.py's weights
+struct BwdCoef {
+    float cp, cs, k1, k2, mf, mw;
+};
+__device__ __forceinline__ BwdCoef bwd_coef(const LossParams& p, const Strip& st, const double* __restrict__ grad4,
+                                            const double* __restrict__ state) {
     const double* sd = state + st.s * OFR_LOSS_STATE_DOUBLES;
     const double wi = 0.05 * (double)(st.s + 1), inv_n = 1.0 / (double)p.n, Bd = (double)p.B;
     const double gP = grad4[0] + grad4[3], gC = grad4[1] + grad4[3], gS = grad4[2] + grad4[3];
-    const float cp = (float)(gP * inv_n * p.gamma * wi / Bd);            // d total / d photometric-sum
-    const float cs = (float)(gS * inv_n * p.lamb_da * wi / (2.0 * Bd));  // d total / d smoothness-sum
+    BwdCoef c;
+    c.cp = (float)(gP * inv_n * p.gamma * wi / Bd);            // d total / d photometric-sum
+    c.cs = (float)(gS * inv_n * p.lamb_da * wi / (2.0 * Bd));  // d total / d smoothness-sum
     // NCC: d(1 - corr)/dw_i = -(1/B) * [ vy_i / sqrt(sxx*syy) - sxy * vx_i / (sxx^1.5 * syy^0.5) ]
     const double N = sd[S_N], mw = sd[S_SW] / N, mf = sd[S_SF] / N;
     const double sxx = sd[S_SWW] - N * mw * mw, syy = sd[S_SFF] - N * mf * mf, sxy = sd[S_SWF] - N * mw * mf;
     const bool degenerate = sd[S_DEGENERATE] != 0.0;
     const double cc = degenerate ? 0.0 : -(gC * inv_n * p.zeta * wi / Bd);
-    const float k1 = degenerate ? 0.f : (float)(cc / (sqrt(sxx) * sqrt(syy)));
-    const float k2 = degenerate ? 0.f : (float)(cc * sxy / (sxx * sqrt(sxx) * sqrt(syy)));
+    c.k1 = degenerate ? 0.f : (float)(cc / (sqrt(sxx) * sqrt(syy)));
+    c.k2 = degenerate ? 0.f : (float)(cc * sxy / (sxx * sqrt(sxx) * sqrt(syy)));
+    c.mf = (float)mf, c.mw = (float)mw;
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const __grid_constant__ LossParams p,
+                                                            const double* __restrict__ grad4,
+                                                            const double* __restrict__ state) {
+    const Strip st = strip_of_cta(p);
+    const BwdCoef c = bwd_coef(p, st, grad4, state);
     if (p.sc[st.s].w % 4 == 0)
-        bwd_body<4>(p, st, cp, cs, k1, k2, (float)mf, (float)mw);
+        bwd_body<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
     else
-        bwd_body<1>(p, st, cp, cs, k1, k2, (float)mf, (float)mw);
+        bwd_body<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+}
+
+__global__ void __launch_bounds__(kThreads, 2) regloss_bwd_kernel(const __grid_constant__ LossParams p,
+                                                                  const double* __restrict__ grad4,
+                                                                  const double* __restrict__ state) {
+    const Strip st = strip_of_cta(p);
+    const BwdCoef c = bwd_coef(p, st, grad4, state);
+    if (p.sc[st.s].w % 4 == 0)
+        bwd_body_fused<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    else
+        bwd_body_fused<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
 }
 
 int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const ofr_loss_scale_t* scales, int n,
@@ -526,7 +674,7 @@ extern "C" int ofr_loss_fwd(const float* fixed, int B, int Hs, int Ws, const ofr
     if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < ws_bytes_for(p.cta_begin[n_scales])) return OFR_EWORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     double* partials = (double*)ws;
-    loss_partial_kernel<<<p.cta_begin[n_scales], kThreads, 0, st>>>(p, partials);
+    loss_partial_kernel<false><<<p.cta_begin[n_scales], kThreads, 0, st>>>(p, partials);
     OFR_LAUNCH_CHECK();
     loss_final_kernel<<<1, 1024, 0, st>>>(p, partials, state, out4);
     OFR_LAUNCH_CHECK();
@@ -541,6 +689,69 @@ extern "C" int ofr_loss_bwd(const float* fixed, int B, int Hs, int Ws, const ofr
     if (rc != OFR_OK) return rc;
     if (!grad4 || !state) return OFR_EINVAL;
     loss_bwd_kernel<<<p.cta_begin[n_scales], kThreads, 0, (cudaStream_t)stream>>>(p, grad4, state);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+// ------------------------------------------------------------------------------------ fused registration loss
+namespace {
+
+// scales of the fused call -> the plain loss's parameters + the stn geometry of every scale (resample2d.cu's make_geom
+// and run_bwd spell the same float32 factors)
+int fill_regloss(LossParams& p, const float* fixed, int B, int Hs, int Ws, const ofr_regloss_scale_t* scales, int n,
+                 double lamb_da, double gamma, double zeta, bool backward) {
+    if (!scales || n < 1 || n > OFR_LOSS_MAX_SCALES) return OFR_EINVAL;
+    ofr_loss_scale_t plain[OFR_LOSS_MAX_SCALES];
+    for (int i = 0; i < n; ++i) {
+        const ofr_regloss_scale_t& s = scales[i];
+        if (!s.moving || !s.warped || (backward && !s.g_flow)) return OFR_EINVAL;
+        plain[i] = ofr_loss_scale_t{s.warped, s.flow, nullptr, s.g_flow, s.h, s.w};
+    }
+    int rc = fill_params(p, fixed, B, Hs, Ws, plain, n, lamb_da, gamma, zeta);
+    if (rc != OFR_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        const ofr_regloss_scale_t& s = scales[i];
+        ScaleDev& d = p.sc[i];
+        d.moving = s.moving;
+        d.warped_out = s.warped;
+        ofr_warp::WarpGeom& g = d.wg;
+        g.B = B, g.C = 1, g.Hin = g.Hf = s.h, g.Win = g.Wf = s.w;
+        g.fs = 1.f;
+        g.fx = (float)(2.0 / s.w);  // models.py:264 builds a FloatTensor from the python floats 2/w, 2/h
+        g.fy = (float)(2.0 / s.h);
+        d.sx = (0.5f * (float)(s.w - 1)) * g.fx;
+        d.sy = (0.5f * (float)(s.h - 1)) * g.fy;
+    }
+    return OFR_OK;
+}
+
+}  // namespace
+
+extern "C" int ofr_regloss_fwd(const float* fixed, int B, int Hs, int Ws, const ofr_regloss_scale_t* scales,
+                               int n_scales, double lamb_da, double gamma, double zeta, double* out4, double* state,
+                               void* ws, size_t ws_bytes, ofr_stream_t stream) {
+    LossParams p;
+    int rc = fill_regloss(p, fixed, B, Hs, Ws, scales, n_scales, lamb_da, gamma, zeta, false);
+    if (rc != OFR_OK) return rc;
+    if (!out4 || !state) return OFR_EINVAL;
+    if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < ws_bytes_for(p.cta_begin[n_scales])) return OFR_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* partials = (double*)ws;
+    loss_partial_kernel<true><<<p.cta_begin[n_scales], kThreads, 0, st>>>(p, partials);
+    OFR_LAUNCH_CHECK();
+    loss_final_kernel<<<1, 1024, 0, st>>>(p, partials, state, out4);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+extern "C" int ofr_regloss_bwd(const float* fixed, int B, int Hs, int Ws, const ofr_regloss_scale_t* scales,
+                               int n_scales, double lamb_da, double gamma, double zeta, const double* grad4,
+                               const double* state, ofr_stream_t stream) {
+    LossParams p;
+    int rc = fill_regloss(p, fixed, B, Hs, Ws, scales, n_scales, lamb_da, gamma, zeta, true);
+    if (rc != OFR_OK) return rc;
+    if (!grad4 || !state) return OFR_EINVAL;
+    regloss_bwd_kernel<<<p.cta_begin[n_scales], kThreads, 0, (cudaStream_t)stream>>>(p, grad4, state);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }

@@ -35,105 +35,13 @@
 #include <climits>
 
 #include "ofr_common.cuh"
+#include "warp_math.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace {
 
-struct WarpGeom {
-    int B, C, Hin, Win, Hf, Wf;
-    float fx, fy;  // STN: float32(2/W), float32(2/H)
-    float fs;      // the flow is multiplied by fs first (1 = plain call; PWCNet.py:214 passes flo * 0.625 ...)
-};
-
-struct Samp {
-    float wx0, wx1, wy0, wy1;  // bilinear weights of the left/right and top/bottom taps
-    int x0, y0;                // floor of the sampling position, clamped to [-2, W] / [-2, H]
-    bool live;                 // false: contributes nothing (PWC mask) -> output 0, no gradient
-};
-
-__device__ __forceinline__ int safe_floor_int(float f, int hi) {
-    // clamp in float first so huge / NaN flows cannot overflow the int conversion
-    f = fminf(fmaxf(f, -2.f), (float)hi);
-    return (int)f;
-}
-
-template <int MODE>
-__device__ __forceinline__ Samp make_samp(int x, int y, float u, float v, const WarpGeom& g) {
-    Samp s;
-    float ix, iy;
-    u = __fmul_rn(u, g.fs);  // exact identity for fs = 1
-    v = __fmul_rn(v, g.fs);
-    if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) {
-        ix = __fadd_rn((float)x, u);
-        iy = __fadd_rn((float)y, v);
-    } else if (MODE == OFR_WARP_STN) {
-        // (x / 2 == x * 0.5 exactly in binary floating point)
-        float gx = __fsub_rn(__fmul_rn(__fadd_rn(u, (float)x), g.fx), 1.f);
-        float gy = __fsub_rn(__fmul_rn(__fadd_rn(v, (float)y), g.fy), 1.f);
-        ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(g.Win - 1));
-        iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(g.Hin - 1));
-    } else {  // PWC
-        const float dx = (float)max(g.Win - 1, 1), dy = (float)max(g.Hin - 1, 1);
-        float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)x, u)), dx), 1.f);
-        float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fadd_rn((float)y, v)), dy), 1.f);
-        ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.Win), 1.f), 0.5f);
-        iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.Hin), 1.f), 0.5f);
-    }
-    const float fxl = floorf(ix), fyl = floorf(iy);
-    if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) {
-        s.wx1 = __fsub_rn(ix, fxl);
-        s.wy1 = __fsub_rn(iy, fyl);
-        s.wx0 = __fsub_rn(1.f, s.wx1);
-        s.wy0 = __fsub_rn(1.f, s.wy1);
-    } else {  // grid_sample: nw = (ix_se - ix) * (iy_se - iy) ...
-        s.wx0 = __fsub_rn(__fadd_rn(fxl, 1.f), ix);
-        s.wx1 = __fsub_rn(ix, fxl);
-        s.wy0 = __fsub_rn(__fadd_rn(fyl, 1.f), iy);
-        s.wy1 = __fsub_rn(iy, fyl);
-    }
-    s.x0 = safe_floor_int(fxl, g.Win);
-    s.y0 = safe_floor_int(fyl, g.Hin);
-    s.live = true;
-    if (MODE == OFR_WARP_PWC) {
-        const bool xl = (unsigned)s.x0 < (unsigned)g.Win, xr = (unsigned)(s.x0 + 1) < (unsigned)g.Win;
-        const bool yt = (unsigned)s.y0 < (unsigned)g.Hin, yb = (unsigned)(s.y0 + 1) < (unsigned)g.Hin;
-        float m = 0.f;  // the warped ones-image, accumulated nw, ne, sw, se like grid_sample
-        if (xl && yt) m = __fadd_rn(m, __fmul_rn(s.wx0, s.wy0));
-        if (xr && yt) m = __fadd_rn(m, __fmul_rn(s.wx1, s.wy0));
-        if (xl && yb) m = __fadd_rn(m, __fmul_rn(s.wx0, s.wy1));
-        if (xr && yb) m = __fadd_rn(m, __fmul_rn(s.wx1, s.wy1));
-        s.live = m >= 0.9999f;
-    }
-    return s;
-}
-
-// Tap column/row for tap offset d in {0,1}: clamped (FLOWNET2) or -1 when outside (zeros padding).
-template <int MODE>
-__device__ __forceinline__ int tap_index(int i0, int d, int n) {
-    int t = i0 + d;
-    if (MODE == OFR_WARP_FLOWNET2 || MODE == OFR_WARP_FLOWNET2_NEAREST) return min(max(t, 0), n - 1);
-    return ((unsigned)t < (unsigned)n) ? t : -1;
-}
-
-// The four taps of a sample as element offsets into one image plane (-1: outside, reads as 0).
-struct TapOff {
-    int tl, tr, bl, br;
-};
-
-template <int MODE>
-__device__ __forceinline__ TapOff tap_offsets(int x0, int y0, int H, int W) {
-    const int xl = tap_index<MODE>(x0, 0, W), xr = tap_index<MODE>(x0, 1, W);
-    const int yt = tap_index<MODE>(y0, 0, H), yb = tap_index<MODE>(y0, 1, H);
-    TapOff t;
-    t.tl = (xl >= 0 && yt >= 0) ? yt * W + xl : -1;
-    t.tr = (xr >= 0 && yt >= 0) ? yt * W + xr : -1;
-    t.bl = (xl >= 0 && yb >= 0) ? yb * W + xl : -1;
-    t.br = (xr >= 0 && yb >= 0) ? yb * W + xr : -1;
-    return t;
-}
-
-__device__ __forceinline__ float fetch(const float* __restrict__ img, int off) { return off >= 0 ? __ldg(img + off) : 0.f; }
+using namespace ofr_warp;
 
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int kFwdThreads = 256;
@@ -146,6 +54,11 @@ constexpr int kPX = 4;        // pixels per thread, stacked in a column
 // bottleneck).  A thread owns kPX vertically adjacent pixels: rows y0 .. y0+kPX-1, whose tap rows overlap in L1.
 // blockIdx.z = image * nchunks + channel chunk.
 // pixels (x, y0 .. y0+kPX-1) of image b, channels [c0, c1)
+// Two bodies.  warp_fwd_body: taps outside the image carry offset -1 and are not loaded (predicated gathers) -- best when
+// a thread loops over many channels (PWC pyramid: the predicates are formed once, masked pixels load nothing).
+// warp_fwd_body_lean: every tap is loaded from a clamped address and out-of-range taps have zero weight -- fewer
+// instructions per pixel, best for the one-channel images (stn of the moving image, FlowNet2's Resample2d), which ncu
+// shows issue-bound (80 % issue slots), not memory-bound.
 template <int MODE>
 __device__ __forceinline__ void warp_fwd_body(const float* __restrict__ in1, const float* __restrict__ flow,
                                               float* __restrict__ out, const WarpGeom& g, int x, int y0, int b, int c0,
@@ -210,6 +123,57 @@ __device__ __forceinline__ void warp_fwd_body(const float* __restrict__ in1, con
 
 
 template <int MODE>
+__device__ __forceinline__ void warp_fwd_body_lean(const float* __restrict__ in1, const float* __restrict__ flow,
+                                              float* __restrict__ out, const WarpGeom& g, int x, int y0, int b, int c0,
+                                              int c1) {
+    const int hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
+    // rows past the bottom edge repeat the last row (loads need no predicate); only their stores are dropped
+    int ro[kPX];
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) ro[k] = min(y0 + k, g.Hf - 1) * g.Wf + x;
+    const float* fu = flow + (size_t)b * 2 * hwf;
+    const float* fv = fu + hwf;
+    float u[kPX], v[kPX];
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+        u[k] = __ldg(fu + ro[k]);
+        v[k] = __ldg(fv + ro[k]);
+    }
+    FwdTaps t[kPX];
+#pragma unroll
+    for (int k = 0; k < kPX; ++k) {
+        const Samp s = make_samp<MODE>(x, y0 + k, u[k], v[k], g);
+        if (MODE == OFR_WARP_FLOWNET2_NEAREST) {  // nearest tap: floor(x + u + 0.5), clamped
+            const float xn = floorf(__fadd_rn(__fadd_rn((float)x, __fmul_rn(u[k], g.fs)), 0.5f));
+            const float yn = floorf(__fadd_rn(__fadd_rn((float)(y0 + k), __fmul_rn(v[k], g.fs)), 0.5f));
+            const int xi = min(max(safe_floor_int(xn, g.Win), 0), g.Win - 1);
+            const int yi = min(max(safe_floor_int(yn, g.Hin), 0), g.Hin - 1);
+            t[k].tl = yi * g.Win + xi;
+        } else {
+            t[k] = fwd_taps<MODE>(s, g.Hin, g.Win);
+        }
+    }
+    const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
+    float* o = out + ((size_t)b * g.C + c0) * hwf;
+#pragma unroll 2
+    for (int c = c0; c < c1; ++c, img += hwi, o += hwf) {
+        float r[kPX];
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) {
+            if (MODE == OFR_WARP_FLOWNET2_NEAREST) {
+                r[k] = __ldg(img + t[k].tl);
+            } else {
+                r[k] = tap_sum(img, t[k]);  // (PWC: the weights of a masked pixel are all 0)
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPX; ++k)
+            if (y0 + k < g.Hf) __stcs(o + ro[k], r[k]);
+    }
+}
+
+
+template <int MODE, bool LEAN>
 __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const float* __restrict__ in1,
                                                                       const float* __restrict__ flow,
                                                                       float* __restrict__ out, WarpGeom g, int nchunks) {
@@ -217,9 +181,16 @@ __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const floa
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
     if (x >= g.Wf || y0 >= g.Hf) return;
     for (int z = blockIdx.z; z < g.B * nchunks; z += gridDim.z) {
-        const int b = z / nchunks, chunk = z - b * nchunks;
+        int b = z, chunk = 0;
+        if (nchunks > 1) {
+            b = z / nchunks;
+            chunk = z - b * nchunks;
+        }
         const int c0 = chunk * kFwdChunk;
-        warp_fwd_body<MODE>(in1, flow, out, g, x, y0, b, c0, min(c0 + kFwdChunk, g.C));
+        if (LEAN)
+            warp_fwd_body_lean<MODE>(in1, flow, out, g, x, y0, b, c0, min(c0 + kFwdChunk, g.C));
+        else
+            warp_fwd_body<MODE>(in1, flow, out, g, x, y0, b, c0, min(c0 + kFwdChunk, g.C));
     }
 }
 
@@ -324,7 +295,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stn_multi_kernel(const __grid_
     if (BACKWARD)
         warp_bwd_flow_body<OFR_WARP_STN>(sc.frame, sc.flow, sc.g_out, sc.g_flow, sc.g, sc.sx, sc.sy, x, y0, b);
     else
-        warp_fwd_body<OFR_WARP_STN>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, sc.g.C);
+        warp_fwd_body_lean<OFR_WARP_STN>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, sc.g.C);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: image (+ flow)
@@ -775,7 +746,10 @@ int launch_fwd(const float* in1, const float* flow, float* out, const WarpGeom& 
     const long long gz = (long long)g.B * nchunks;
     dim3 block, grid;
     block_shape(g.Wf, g.Hf, block, grid, (unsigned)(gz < 65535 ? gz : 65535));
-    resample_fwd_kernel<MODE><<<grid, block, 0, st>>>(in1, flow, out, g, nchunks);
+    if (g.C <= 2)
+        resample_fwd_kernel<MODE, true><<<grid, block, 0, st>>>(in1, flow, out, g, nchunks);
+    else
+        resample_fwd_kernel<MODE, false><<<grid, block, 0, st>>>(in1, flow, out, g, nchunks);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }

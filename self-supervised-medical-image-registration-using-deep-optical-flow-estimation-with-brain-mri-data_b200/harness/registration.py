@@ -56,9 +56,11 @@ def synthetic_pairs(batch, size, seed=6, device="cpu", max_shift=8.0):
 class RegistrationStep(nn.Module):
     """predictor + per-scale stn warp + multi-scale loss; ``forward(pair)`` returns (p, c, s, total)."""
 
-    def __init__(self, predictor, stn, loss_fn, stn_multi=None):
-        """``stn_multi(flows, moving)`` (optional) replaces the per-scale ``stn`` loop with one batched call."""
+    def __init__(self, predictor, stn, loss_fn, stn_multi=None, reg_loss=None):
+        """``stn_multi(flows, moving)`` (optional) replaces the per-scale ``stn`` loop with one batched call;
+        ``reg_loss(flows, moving, fixed) -> (terms, warped)`` (optional) replaces warps + loss with the fused call."""
         super().__init__()
+        self._reg_loss = reg_loss
         self.predictor = predictor
         self._stn = stn
         self._stn_multi = stn_multi
@@ -68,6 +70,8 @@ class RegistrationStep(nn.Module):
         flows = list(self.predictor(pair))
         fixed = pair[:, :1].contiguous()
         moving = pair[:, 1:].contiguous()
+        if self._reg_loss is not None:
+            return self._reg_loss(flows, moving, fixed)[0]
         if self._stn_multi is not None:
             warped = self._stn_multi(flows, moving)
         else:

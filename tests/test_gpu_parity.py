@@ -327,6 +327,74 @@ def test_stn_warp_multi_equals_the_per_scale_loop(ofr):
     close(res[1][0][1], ref, atol=1e-5, what="stn multi vs oracle")
 
 
+def test_registration_loss_equals_stn_then_ofeloss(ofr):
+    """registration_loss(flows, moving, fixed) == OFEloss(flows, stn_warp_multi(flows, moving), fixed)
+    (models.py:277 + train.py:56): warped images, the four terms and the flow gradients bit for bit, from each of the
+    four returned terms, over a pyramid with ragged (VEC=1) and tiny scales; and against the float64 oracle."""
+    B = 3
+    fixed = torch.rand(B, 1, 40, 36, generator=gen(80)).to(DEV)
+    moving = torch.rand(B, 1, 40, 36, generator=gen(81)).to(DEV)
+    sizes = [(40, 36), (20, 18), (12, 8), (5, 5), (2, 3)]
+    flows = [(torch.randn(B, 2, h, w, generator=gen(82 + i)) * 2).to(DEV) for i, (h, w) in enumerate(sizes)]
+    for k in range(4):
+        res = []
+        for fused in (False, True):
+            fl = [f.clone().requires_grad_(True) for f in flows]
+            if fused:
+                terms, warped = ofr.registration_loss(fl, moving, fixed, lamb_da=0.7, gamma=90.0, zeta=110.0)
+                assert not any(w.requires_grad for w in warped)
+            else:
+                warped = ofr.stn_warp_multi(fl, moving)
+                terms = ofr.OFEloss(fl, warped, fixed, lamb_da=0.7, gamma=90.0, zeta=110.0)
+            grads = torch.autograd.grad(terms[k], fl, allow_unused=True)
+            res.append(([t.detach() for t in terms], [w.detach() for w in warped], grads))
+        for a, b in zip(res[0][0], res[1][0]):
+            assert torch.equal(a, b), f"term differs (backward from term {k})"
+        for a, b in zip(res[0][1], res[1][1]):
+            assert torch.equal(a, b), "warped image differs"
+        for i, (a, b) in enumerate(zip(res[0][2], res[1][2])):
+            if a is None:  # the smoothness term alone does not reach the warp; fused returns zeros + smoothness
+                continue
+            assert torch.equal(a, b), f"flow gradient {i} differs (backward from term {k})"
+    # oracle: stn + OFEloss on the CPU; values against float64, gradients against the reference's own float32 chain
+    # (the float32 sampling positions move the warped image by ~3e-6, which the |x|^-0.5 photometric derivative
+    # amplifies beyond 1e-4 wherever |fixed - warped| is a few 1e-3: float32 and float64 runs of the REFERENCE differ
+    # by 6e-4 on these inputs)
+    fd = [f.cpu().double().requires_grad_(True) for f in flows]
+    wd = [oracle.stn_warp(f, moving.cpu().double()) for f in fd]
+    rres = oracle.ofe_loss(fd, wd, fixed.cpu().double())
+    f32 = [f.cpu().requires_grad_(True) for f in flows]
+    w32 = [oracle.stn_warp(f, moving.cpu()) for f in f32]
+    rg = torch.autograd.grad(oracle.ofe_loss(f32, w32, fixed.cpu())[3], f32)
+    fl = [f.clone().requires_grad_(True) for f in flows]
+    terms, warped = ofr.registration_loss(fl, moving, fixed)
+    gg = torch.autograd.grad(terms[3], fl)
+    np.testing.assert_allclose([t.item() for t in terms], [t.item() for t in rres], rtol=2e-6)
+    for i, (w, r) in enumerate(zip(warped, wd)):
+        close(w, r.detach(), atol=1e-5, what=f"regloss warped[{i}]")
+    for i, (g, r) in enumerate(zip(gg, rg)):
+        # d/dx (x^2 + 1e-18)^0.25 behaves like |x|^-0.5 near 0: where fixed and warped agree to ~1e-3 the photometric
+        # gradient (and with it the flow gradient of that pixel) is ill-conditioned in float32, in the reference too
+        h, w = g.shape[2:]
+        diff = torch.nn.functional.interpolate(fixed, (h, w), mode="bilinear", align_corners=False) - warped[i]
+        keep = (diff.abs() > 1e-3).double().cpu()
+        close(g.double().cpu() * keep, r.double() * keep, atol=1e-6, rtol=1e-4, what=f"regloss gflow[{i}]")
+
+
+def test_registration_loss_argument_errors(ofr):
+    fixed = torch.rand(2, 1, 16, 16).to(DEV)
+    flow = torch.zeros(2, 2, 16, 16).to(DEV)
+    with pytest.raises(ValueError):
+        ofr.registration_loss([flow], fixed.clone().requires_grad_(True), fixed)
+    with pytest.raises(ValueError):
+        ofr.registration_loss([], fixed, fixed)
+    with pytest.raises(ValueError):
+        ofr.registration_loss([flow[:, :1]], fixed, fixed)
+    # zero flow: the warped image is the stn identity resampling of the moving image, x * (W - 1) / W
+    terms, warped = ofr.registration_loss([flow], fixed, fixed)
+    close(warped[0], oracle.stn_warp(flow.cpu(), fixed.cpu()), atol=1e-6, what="regloss zero flow")
+
+
 # =============================================================================== loss
 def test_loss_vs_reference_golden(ofr, golden):
     g = golden("loss")

@@ -137,6 +137,39 @@ def cases(B, S, only=".*", dry=False):
                     lambda: (keep, L.ofr_loss_bwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(g4), P(state),
                                                   stream()))[1]))
 
+    def regloss(n):
+        names = [f"regloss_fwd n{n} {S}x{S}", f"regloss_bwd n{n} {S}x{S}"]
+        if dry:
+            out.extend((n, 0, 0, None) for n in names)
+            return
+        if not any(want(n) for n in names):
+            return
+        fixed = torch.rand(B, 1, S, S, device=DEV)
+        sizes = [S >> i for i in range(n)]
+        flows = [torch.randn(B, 2, s, s, device=DEV) * 4.0 for s in sizes]
+        movs = [torch.rand(B, 1, s, s, device=DEV) for s in sizes]
+        warps = [torch.rand(B, 1, s, s, device=DEV) for s in sizes]
+        gfl = [torch.empty_like(f) for f in flows]
+        arr = (_lib.RegLossScale * n)()
+        for i in range(n):
+            arr[i].moving, arr[i].flow = movs[i].data_ptr(), flows[i].data_ptr()
+            arr[i].warped, arr[i].g_flow = warps[i].data_ptr(), gfl[i].data_ptr()
+            arr[i].h = arr[i].w = sizes[i]
+        out4 = torch.empty(4, dtype=torch.float64, device=DEV)
+        state = torch.empty(n * 16, dtype=torch.float64, device=DEV)
+        g4 = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=DEV)
+        wsb = int(L.ofr_loss_workspace(n))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        px = sum(s * s for s in sizes)
+        keep = (fixed, flows, movs, warps, gfl, arr)
+        L.ofr_regloss_fwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(out4), P(state), P(ws), wsb, stream())
+        out.append((f"regloss_fwd n{n} {S}x{S}", 4 * B * (4 * px + S * S), 0,
+                    lambda: (keep, L.ofr_regloss_fwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(out4), P(state),
+                                                     P(ws), wsb, stream()))[1]))
+        out.append((f"regloss_bwd n{n} {S}x{S}", 4 * B * (6 * px + S * S), 0,
+                    lambda: (keep, L.ofr_regloss_bwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(g4), P(state),
+                                                     stream()))[1]))
+
     # PWC-Net pyramid (PWCNet.py:200-259): levels 2..6
     for lvl, C in [(2, 32), (3, 64), (4, 96), (5, 128), (6, 196)]:
         corr(f"pwc_l{lvl}", C, S >> lvl, 4, 4, 1)
@@ -150,6 +183,7 @@ def cases(B, S, only=".*", dry=False):
     chnorm(1, S)
     chnorm(2, S)
     loss(7)
+    regloss(7)
     return [c for c in out if want(c[0])]
 
 
