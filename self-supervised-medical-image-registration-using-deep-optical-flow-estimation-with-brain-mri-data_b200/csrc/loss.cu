@@ -216,6 +216,8 @@ __device__ __forceinline__ void partial_body(const LossParams& p, const Strip& s
     const float* wp = sc.warped + (size_t)st.b * hw;
     const float* fu = sc.flow + (size_t)st.b * 2 * hw;
     const float* fvp = fu + hw;
+    const float* mv = FUSED ? sc.moving + (size_t)st.b * hw : nullptr;
+    float* wo = FUSED ? sc.warped_out + (size_t)st.b * hw : nullptr;
     const Walk wk = walk_of_thread(sc, st);
     if (wk.ya >= wk.yb) return;
     for (int g = wk.gx; g < gw; g += wk.tx_n) {
@@ -231,10 +233,9 @@ __device__ __forceinline__ void partial_body(const LossParams& p, const Strip& s
         for (int y = wk.ya; y < wk.yb; ++y, o += w) {
             float wv[VEC], fx[VEC], ud[VEC], vd[VEC];
             if (FUSED) {
-                const float* mv = sc.moving + (size_t)st.b * hw;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) wv[k] = stn_value(mv, x + k, y, u[k], v[k], sc.wg);
-                store_vec<VEC>(sc.warped_out + (size_t)st.b * hw + o, wv);
+                store_vec<VEC>(wo + o, wv);
             } else {
                 load_vec<VEC>(wp + o, wv);
             }
@@ -488,11 +489,11 @@ __device__ __forceinline__ void bwd_body_fused(const LossParams& p, const Strip&
     const int h = sc.h, w = sc.w, gw = w / VEC, hw = h * w;
     const float sh = (float)p.Hs / (float)h, sw = (float)p.Ws / (float)w;
     const bool ident = VEC == 4 && h == p.Hs && w == p.Ws && (p.Ws % 4) == 0 && (reinterpret_cast<uintptr_t>(p.fixed) & 15u) == 0;
-    const float* fixed = p.fixed + (size_t)st.b * p.Hs * p.Ws;
-    const float* wp = sc.warped + (size_t)st.b * hw;
-    const float* mv = sc.moving + (size_t)st.b * hw;
-    const float* f0 = sc.flow + (size_t)st.b * 2 * hw;
-    float* gfp = sc.g_flow + (size_t)st.b * 2 * hw;
+    const float* fixed = ofr_warp::opaque_ptr(p.fixed + (size_t)st.b * p.Hs * p.Ws);
+    const float* wp = ofr_warp::opaque_ptr(sc.warped + (size_t)st.b * hw);
+    const float* mv = ofr_warp::opaque_ptr(sc.moving + (size_t)st.b * hw);
+    const float* f0 = ofr_warp::opaque_ptr(sc.flow + (size_t)st.b * 2 * hw);
+    float* gfp = ofr_warp::opaque_ptr(sc.g_flow + (size_t)st.b * 2 * hw);
     const Walk wk = walk_of_thread(sc, st);
     if (wk.ya >= wk.yb) return;
     for (int g = wk.gx; g < gw; g += wk.tx_n) {
@@ -529,8 +530,8 @@ __device__ __forceinline__ void bwd_body_fused(const LossParams& p, const Strip&
         const bool has_right = x + VEC < w, has_left = x > 0;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const float* f = f0 + c * hw;
-            float* gp = gfp + c * hw;
+            const float* f = ofr_warp::opaque_ptr(f0 + c * hw);
+            float* gp = ofr_warp::opaque_ptr(gfp + c * hw);
             float v[VEC], up[VEC];  // up[k] = psi(v[y-1][k] - v[y][k]), carried from the previous row
             {
                 const int o = wk.ya * w + x;

@@ -100,7 +100,7 @@ __device__ __forceinline__ void warp_fwd_body(const float* __restrict__ in1, con
         const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
         float* o = out + ((size_t)b * g.C + c0) * hwf + rem;
 #pragma unroll 2
-        for (int c = c0; c < c1; ++c, img += hwi, o += hwf) {
+        for (int c = c0; c < c1; ++c, img = img + hwi, o = o + hwf) {
             float r[kPX];
 #pragma unroll
             for (int k = 0; k < kPX; ++k) {
@@ -131,8 +131,8 @@ __device__ __forceinline__ void warp_fwd_body_lean(const float* __restrict__ in1
     int ro[kPX];
 #pragma unroll
     for (int k = 0; k < kPX; ++k) ro[k] = min(y0 + k, g.Hf - 1) * g.Wf + x;
-    const float* fu = flow + (size_t)b * 2 * hwf;
-    const float* fv = fu + hwf;
+    const float* fu = opaque_ptr(flow + (size_t)b * 2 * hwf);
+    const float* fv = opaque_ptr(fu + hwf);
     float u[kPX], v[kPX];
 #pragma unroll
     for (int k = 0; k < kPX; ++k) {
@@ -153,10 +153,10 @@ __device__ __forceinline__ void warp_fwd_body_lean(const float* __restrict__ in1
             t[k] = fwd_taps<MODE>(s, g.Hin, g.Win);
         }
     }
-    const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
-    float* o = out + ((size_t)b * g.C + c0) * hwf;
+    const float* img = opaque_ptr(in1 + ((size_t)b * g.C + c0) * hwi);
+    float* o = opaque_ptr(out + ((size_t)b * g.C + c0) * hwf);
 #pragma unroll 2
-    for (int c = c0; c < c1; ++c, img += hwi, o += hwf) {
+    for (int c = c0; c < c1; ++c, img = opaque_ptr(img + hwi), o = opaque_ptr(o + hwf)) {
         float r[kPX];
 #pragma unroll
         for (int k = 0; k < kPX; ++k) {
@@ -227,7 +227,7 @@ __device__ __forceinline__ void warp_bwd_flow_body(const float* __restrict__ in1
         for (int k = 0; k < kPX; ++k) ax[k] = ay[k] = 0.f;
         const float* img = in1 + (size_t)b * g.C * hwi;
         const float* gp = gO + (size_t)b * g.C * hwf + rem;
-        for (int c = 0; c < g.C; ++c, img += hwi, gp += hwf) {
+        for (int c = 0; c < g.C; ++c, img = img + hwi, gp = gp + hwf) {
 #pragma unroll
             for (int k = 0; k < kPX; ++k) {
                 const float go = ok[k] ? __ldg(gp + k * g.Wf) : 0.f;

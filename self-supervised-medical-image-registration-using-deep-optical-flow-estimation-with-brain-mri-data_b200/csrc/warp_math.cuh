@@ -99,6 +99,16 @@ __device__ __forceinline__ TapOff tap_offsets(int x0, int y0, int H, int W) {
     return t;
 }
 
+// A pointer the compiler must keep as one 64-bit register pair: element accesses p[int offset] then cost one IMAD.WIDE.
+// (Left alone, nvcc folds kernel-argument pointers plus image/plane offsets into a 64-bit element index and rebuilds
+// every address with IADD3 + LEA.HI.X.SX32 + LEA + LEA.HI.X -- four issue slots per load in kernels that are issue-bound.)
+template <class T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {
+    unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    asm volatile("" : "+l"(v));
+    return reinterpret_cast<T*>(v);
+}
+
 __device__ __forceinline__ float fetch(const float* __restrict__ img, int off) { return off >= 0 ? __ldg(img + off) : 0.f; }
 
 // Forward taps: four ALWAYS-LOADABLE element offsets and the four bilinear products.  Border mode (FlowNet2): the taps
