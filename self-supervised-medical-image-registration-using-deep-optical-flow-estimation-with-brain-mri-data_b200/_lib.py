@@ -13,7 +13,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libofr_b200.so")
-SOURCES = ["abi.cu", "channelnorm.cu", "resample2d.cu", "correlation.cu", "correlation_tma.cu", "loss.cu"]
+SOURCES = ["abi.cu", "channelnorm.cu", "resample2d.cu", "correlation.cu", "correlation_tma.cu", "correlation_umma.cu", "loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared"]
 

@@ -716,8 +716,12 @@ int corr_fwd_tma(const float* f1, const float* f2, float* out, const CorrGeom& g
         if (ks > 1) return launch_fwd_split<4, 4, 8, 2, 8, 4>(f1, f2, out, g, ks, st);
         return launch_fwd<4, 4, 8, 2, 8, 4>(f1, f2, out, g, st);
     }
-    if (applicable(g, 10, f1, f2, out))
+    if (applicable(g, 10, f1, f2, out)) {
+        // the 21 x 21 window is FMA-bound (59 FLOP/B): Gram tiles on the tensor cores (3xTF32, TMEM accumulators)
+        const int rc = ofr::corr_fwd_umma(f1, f2, out, g, st);
+        if (rc != OFR_ENOTSUP) return rc;
         return launch_fwd<10, 8, 4, 2, 8, 3>(f1, f2, out, g, st);                 // 4 x 16 tile, 192 threads (3 x 8 tj lanes)
+    }
     return OFR_ENOTSUP;
 }
 

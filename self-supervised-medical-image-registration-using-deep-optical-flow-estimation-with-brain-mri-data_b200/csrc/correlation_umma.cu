@@ -1,0 +1,304 @@
+// Correlation forward for the FlowNetC window on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Scope: the stride-1 class-image problem the polyphase split of Correlation(20,1,20,1,2) produces
+// (flownet2/networks/FlowNetC.py:31,88): k = 1, s1 = s2 = 1, pad = md = 10, window 21 x 21 = 441 displacements, C = 256.
+// This is the configuration SURVEY.md 8(a1) marks FMA-bound (59 FLOP/B); the register-tiled FMA kernel
+// (correlation_tma.cu, R = 10) reaches 34 % of the FP32 pipe because the 21 x 21 halo is 13x the tile.
+//
+// Formulation: for a tile of 128 pixels p (8 rows x 16) the cost volume is a band of the Gram matrix
+//     S[p, q] = sum_c f1[c, p] * f2[c, q],          out[(dy, dx), p] = S[p, p + (dy, dx)] / C
+// over the 28 x 36 neighbourhood q of the tile.  S is computed as four GEMMs M = 128, N = 256 (7 neighbourhood rows of
+// 36 columns = 252, padded), K = C in stages of 16 channels:
+//   * operands are written by the CTA's threads into the canonical K-major no-swizzle layout (8 x 16 B core matrices),
+//     out-of-image neighbours as zeros (= the operator's zero padding), each value split into a TF32 "hi" part
+//     (cvt.rna) and the exact remainder "lo"; the product is hi*hi + hi*lo + lo*hi (3xTF32) accumulated in FP32 in TMEM:
+//     measured max error 4e-6 on sums of magnitude 8 (tools/micro/tf32_umma.cu), i.e. < 1e-7 after the 1/C scaling --
+//     inside the 1e-5 bound of the operator; one TF32 product alone (7e-4) is not;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::tf32); tcgen05.commit on an mbarrier per stage buffer
+//     tells the threads when a buffer may be overwritten; the global loads of stage s+1 are in flight while stage s is
+//     written and multiplied;
+//   * epilogue: warps 0-3 read their 32 TMEM lanes (= pixels) one neighbourhood row at a time (36 columns), pick the
+//     21-wide band through a per-warp shared-memory transposition (the band offset depends on the pixel's column, a
+//     register index must not) and store whole 64-byte row segments of each displacement plane.
+// Two CTAs fit an SM (100 KB of shared memory, 256 of the 512 TMEM columns each): one CTA's operand staging and
+// epilogue overlap the other's MMAs.  44 % of S is wanted and the split costs 3 MMAs: 6.9x the useful MACs on a pipe
+// measured at 1096 TFLOP/s (tf32, N = 256) against 72 TFLOP/s of FP32 FMA.
+#include "corr_internal.cuh"
+
+#include <cstdlib>
+
+namespace {
+
+constexpr int UM = 128;          // pixels per tile = MMA M
+constexpr int UN = 256;          // neighbourhood positions per chunk (252 used) = MMA N
+constexpr int UKT = 16;          // channels per stage (two K = 8 MMA steps)
+constexpr int UR = 10;           // displacement radius
+constexpr int UD = 2 * UR + 1;   // 21
+constexpr int UTH = 8, UTW = 16; // tile
+constexpr int UNW = UTW + 2 * UR;           // 36 neighbourhood columns
+constexpr int UROWS = 7;                    // neighbourhood rows per chunk
+constexpr int UCHUNKS = (UTH + 2 * UR) / UROWS;  // 4
+constexpr int UTHREADS = 256;
+constexpr int A_FLOATS = UM * UKT, B_FLOATS = UN * UKT;
+constexpr int STAGE_FLOATS = 2 * (A_FLOATS + B_FLOATS);  // hi + lo
+constexpr int EBUF_FLOATS = 4 * UD * 32;
+constexpr size_t USMEM = sizeof(float) * (2 * STAGE_FLOATS + EBUF_FLOATS) + 1024;
+static_assert(UCHUNKS * UROWS == UTH + 2 * UR && UROWS * UNW <= UN, "chunking");
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: element (row r, 16-byte chunk j along K) at j * LBO + r * 16
+// (core matrix = 8 rows x 16 B contiguous, SBO = 128 B between 8-row groups)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version of sm_100
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// wait for the phase with the given parity; a barrier that never completes (it cannot, unless the MMA was rejected)
+// traps after ~2 s instead of hanging the device
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(s32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+    hi = __uint_as_float(hb);
+    lo = x - hi;  // exact
+}
+
+__global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float* __restrict__ f1,
+                                                                   const float* __restrict__ f2,
+                                                                   float* __restrict__ out, ofr::CorrGeom g,
+                                                                   int tiles_x, int tiles_y) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* stages = reinterpret_cast<float*>(smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u));
+    float* ebuf = stages + 2 * STAGE_FLOATS;
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x;
+    bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = txi * UTW, y0 = tyi * UTH;
+    const int H = g.H, W = g.W, hw = H * W, C = g.C;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)),
+                     "r"((uint32_t)UN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    // D = F32 (bit 4), A = B = TF32 (2 at bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+    constexpr uint32_t LBO_A = UM * 16, LBO_B = UN * 16;
+
+    // staging tasks: one task = one row of an operand (a pixel) x 4 consecutive channels = one 16-byte chunk
+    //   A: 128 pixels x 4 chunks = 512 tasks (2 per thread);  B: 256 positions x 4 chunks = 1024 tasks (4 per thread)
+    const float* f1b = f1 + (size_t)b * C * hw;
+    const float* f2b = f2 + (size_t)b * C * hw;
+    int a_src[2], a_dst[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int t = tid + UTHREADS * i, m = t & (UM - 1), kq = t >> 7;
+        a_src[i] = kq * 4 * hw + (y0 + (m >> 4)) * W + x0 + (m & 15);
+        a_dst[i] = kq * (UM * 4) + m * 4;
+    }
+    int b_dst[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = tid + UTHREADS * i, j = t & (UN - 1), kq = t >> 8;
+        b_dst[i] = kq * (UN * 4) + j * 4;
+    }
+
+    const int nstages = C / UKT;
+    uint32_t it = 0;  // stages issued so far (buffer = it & 1)
+    for (int n = 0; n < UCHUNKS; ++n) {
+        int b_src[4];  // element offset of the task's neighbour inside one channel plane, or -1 (zero padding)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = tid + UTHREADS * i, j = t & (UN - 1), kq = t >> 8;
+            const int rc = j / UNW, cc = j - rc * UNW;
+            const int yy = y0 - UR + n * UROWS + rc, xx = x0 - UR + cc;
+            const bool in = j < UROWS * UNW && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
+            b_src[i] = in ? kq * 4 * hw + yy * W + xx : -1;
+        }
+        float pa[2][4], pb[4][4];
+        auto load = [&](int s) {
+            const float* p1 = f1b + (size_t)s * UKT * hw;
+            const float* p2 = f2b + (size_t)s * UKT * hw;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pa[i][c] = __ldg(p1 + a_src[i] + c * hw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pb[i][c] = b_src[i] >= 0 ? __ldg(p2 + b_src[i] + c * hw) : 0.f;
+        };
+        load(0);
+        for (int s = 0; s < nstages; ++s, ++it) {
+            const uint32_t buf = it & 1u;
+            float* sAh = stages + buf * STAGE_FLOATS;
+            float* sAl = sAh + A_FLOATS;
+            float* sBh = sAl + A_FLOATS;
+            float* sBl = sBh + B_FLOATS;
+            if (it >= 2) mbar_wait_or_trap(&bars[buf], ((it >> 1) - 1u) & 1u);  // the MMAs that read this buffer are done
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                float4 h, l;
+                split_tf32(pa[i][0], h.x, l.x);
+                split_tf32(pa[i][1], h.y, l.y);
+                split_tf32(pa[i][2], h.z, l.z);
+                split_tf32(pa[i][3], h.w, l.w);
+                *reinterpret_cast<float4*>(sAh + a_dst[i]) = h;
+                *reinterpret_cast<float4*>(sAl + a_dst[i]) = l;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 h, l;
+                split_tf32(pb[i][0], h.x, l.x);
+                split_tf32(pb[i][1], h.y, l.y);
+                split_tf32(pb[i][2], h.z, l.z);
+                split_tf32(pb[i][3], h.w, l.w);
+                *reinterpret_cast<float4*>(sBh + b_dst[i]) = h;
+                *reinterpret_cast<float4*>(sBl + b_dst[i]) = l;
+            }
+            if (s + 1 < nstages) load(s + 1);  // in flight while this stage is multiplied
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int ks = 0; ks < UKT / 8; ++ks) {
+                    const uint64_t dAh = umma_desc(s32(sAh) + ks * 2 * LBO_A, LBO_A), dAl = umma_desc(s32(sAl) + ks * 2 * LBO_A, LBO_A);
+                    const uint64_t dBh = umma_desc(s32(sBh) + ks * 2 * LBO_B, LBO_B), dBl = umma_desc(s32(sBl) + ks * 2 * LBO_B, LBO_B);
+                    umma_tf32(tmem_d, dAh, dBh, idesc, (s | ks) ? 1u : 0u);
+                    umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
+                    umma_tf32(tmem_d, dAl, dBh, idesc, 1u);
+                }
+                // arrives on the buffer's barrier when these (and all earlier) MMAs have completed
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bars[buf]))
+                             : "memory");
+            }
+        }
+        // the chunk's accumulators are complete when the last stage's commit has arrived
+        mbar_wait_or_trap(&bars[(it - 1u) & 1u], ((it - 1u) >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp < 4) {
+            const int yp = 2 * warp + (lane >> 4), xp = lane & 15;
+            float* eb = ebuf + warp * (UD * 32);
+            const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int rc = 0; rc < UROWS; ++rc) {
+                const int dy = n * UROWS + rc - yp;
+                const bool valid = (unsigned)dy < (unsigned)UD;
+                uint32_t v[UNW];
+                const uint32_t ta = trow + rc * UNW;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(ta)
+                    : "memory");
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35])
+                             : "r"(ta + 32)
+                             : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // band of this pixel: neighbourhood columns xp .. xp + 20 -> displacement column dx = j - xp
+#pragma unroll
+                for (int j = 0; j < UNW; ++j) {
+                    const int dx = j - xp;
+                    if (valid && (unsigned)dx < (unsigned)UD) eb[dx * 32 + lane] = ofr::corr_out(__uint_as_float(v[j]), g);
+                }
+                __syncwarp();
+                if (valid) {
+                    float* o = out + (((size_t)b * (UD * UD) + dy * UD) * H + y0 + yp) * W + x0 + xp;
+#pragma unroll
+                    for (int dx = 0; dx < UD; ++dx) __stcs(o + (size_t)dx * hw, eb[dx * 32 + lane]);
+                }
+                __syncwarp();
+            }
+        }
+        // the next chunk's first MMA overwrites the accumulators: every reader must be done
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)UN) : "memory");
+}
+
+}  // namespace
+
+namespace ofr {
+
+// Class-image correlation (k = 1, s1 = s2 = 1, pad = md = 10) on the tensor cores.  OFR_ENOTSUP (nothing launched) when
+// the geometry does not tile (the caller then uses the FMA kernels).  OFR_CORR_UMMA=0 in the environment disables it
+// (A/B measurements only).
+int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
+    static const bool enabled = [] {
+        const char* e = getenv("OFR_CORR_UMMA");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled) return OFR_ENOTSUP;
+    if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
+    if ((g.W % UTW) || (g.H % UTH) || (g.C % UKT) || g.C < UKT) return OFR_ENOTSUP;
+    if ((long long)g.C * g.H * g.W >= (1ll << 30)) return OFR_ENOTSUP;
+    const int tiles_x = g.W / UTW, tiles_y = g.H / UTH;
+    const long long nblk = (long long)tiles_x * tiles_y * g.B;
+    if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
+    OFR_CUDA(cudaFuncSetAttribute(corr_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)USMEM));
+    corr_fwd_umma_kernel<<<(unsigned)nblk, UTHREADS, USMEM, st>>>(f1, f2, out, g, tiles_x, tiles_y);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+}  // namespace ofr

@@ -84,6 +84,7 @@ CORR_CASES = {
     "pwc_wide": (1, 8, 6, 136, 4, 1, 4, 1, 1),          # several x tiles with a ragged last one
     "flownetc": (1, 256, 32, 32, 20, 1, 20, 1, 2),
     "flownetc_small": (2, 20, 12, 16, 20, 1, 20, 1, 2),
+    "flownetc_tc": (2, 48, 32, 64, 20, 1, 20, 1, 2),    # class images 16 x 32: tensor-core forward, 2 x 2 tiles, 3 K stages
     "generic_w_odd": (2, 5, 9, 11, 4, 1, 4, 1, 1),      # W % 4 != 0 -> generic kernels
     "generic_k3": (1, 3, 9, 10, 3, 3, 2, 1, 1),
     "generic_s1": (1, 4, 12, 12, 4, 1, 4, 2, 2),
@@ -125,6 +126,33 @@ def test_correlation_one_hot(ofr):
         nz = out.nonzero()
         assert nz.shape[0] == 1 and tuple(nz[0].tolist()) == (0, (tj + r) * D + (ti + r), y0, x0)
         assert abs(out[tuple(nz[0].tolist())].item() - 6.0 / 4) < 1e-7
+
+
+def test_correlation_flownetc_full_size_tensor_core_forward(ofr):
+    """Correlation(20,1,20,1,2) at the FlowNetC shape (B=24, C=256, 64x64: FlowNetC.py:31,88) -- the tcgen05 3xTF32 path
+    -- against the definition evaluated in float64 on the GPU for a sample of displacement planes (centre, corners,
+    mixed), with the fused LeakyReLU; exact on one-hot features; bitwise reproducible."""
+    B, C, H, W, md, s2 = 24, 256, 64, 64, 20, 2
+    g0 = torch.Generator(device=DEV).manual_seed(90)
+    f1 = torch.randn(B, C, H, W, device=DEV, generator=g0)
+    f2 = torch.randn(B, C, H, W, device=DEV, generator=g0)
+    corr = ofr.Correlation(md, 1, md, 1, s2, 1, leaky_relu=0.1)
+    out = corr(f1, f2)
+    assert torch.equal(out, corr(f1, f2))
+    r, D = md // s2, 2 * (md // s2) + 1
+    f1d, f2d = f1.double(), torch.nn.functional.pad(f2.double(), (md, md, md, md))
+    for tj, ti in [(0, 0), (-r, -r), (r, r), (-r, r), (3, -7), (-1, 1), (r, 0), (0, -r)]:
+        sh = f2d[:, :, md + s2 * tj: md + s2 * tj + H, md + s2 * ti: md + s2 * ti + W]
+        ref = torch.nn.functional.leaky_relu((f1d * sh).mean(1), 0.1)
+        close(out[:, (tj + r) * D + (ti + r)], ref, atol=1e-5, what=f"flownetc full-size plane ({tj},{ti})")
+    a = torch.zeros(1, 16, 32, 32, device=DEV)
+    b = torch.zeros(1, 16, 32, 32, device=DEV)
+    a[0, 5, 9, 20] = 2.0
+    b[0, 5, 9 + s2 * 4, 20 - s2 * 9] = 3.0
+    o = ofr.Correlation(md, 1, md, 1, s2, 1)(a, b)
+    nz = o.nonzero()
+    assert nz.shape[0] == 1 and tuple(nz[0].tolist()) == (0, (4 + r) * D + (-9 + r), 9, 20)
+    assert o[tuple(nz[0].tolist())].item() == 6.0 / 16
 
 
 def test_correlation_is_reproducible_and_skips_unneeded_grads(ofr):
