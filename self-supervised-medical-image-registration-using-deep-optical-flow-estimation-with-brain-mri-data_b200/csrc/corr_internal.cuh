@@ -27,5 +27,7 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
 // tcgen05 / TMEM forward for the class-image problem of the FlowNetC window (pad = md = 10 after the polyphase split):
 // correlation_umma.cu.  OFR_ENOTSUP when the geometry does not tile.
 int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st);
+int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
+                  cudaStream_t st);
 
 }  // namespace ofr

@@ -732,6 +732,10 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
         return dispatch_bwd4(f1, f2, gO, gI1, gI2, g, st);
     }
     if (applicable(g, 10, f1, f2, gO)) {
+        {  // FlowNetC window: banded GEMMs on the tensor cores (correlation_umma.cu)
+            const int rc = ofr::corr_bwd_umma(f1, f2, gO, gI1, gI2, g, st);
+            if (rc != OFR_ENOTSUP) return rc;
+        }
         // R = 10 (class images of FlowNetC, 16 x 16 or 32 x 32): 8 x 16 tiles, 8 channel groups x 4 channels, 7
         // x-displacements per register sweep
         return launch_bwd<10, 8, 2, 8, 7, 2, 32>(f1, f2, gO, gI1, gI2, g, st);

@@ -276,19 +276,239 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)UN) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward
+// Both gradients are the same GEMM with the roles of the operands exchanged.  For a tile of 128 target pixels t and its
+// 28 x 36 neighbourhood n:
+//     gI1[c, t] = s * sum_n G1[t, n] * f2[c, n],   G1[t, n] = gO[plane(n - t)][t]
+//     gI2[c, t] = s * sum_n G2[t, n] * f1[c, n],   G2[t, n] = gO[plane(t - n)][n]        (n inside the image)
+// M = 128 targets, N = C channels (<= 256: the accumulators are C TMEM columns), K = the neighbourhood, walked one row
+// (36 positions, padded to 40) at a time as two stages of 24 + 16.  The banded operand G is built in shared memory: the
+// gradient rows a neighbourhood row needs (8 tile rows x 21 x-displacements x 16 pixels, whole 64-byte segments of the
+// planes) are loaded into a small buffer R[yp][dx][xp], and A[t][cc] = R[yp][cc - xp][xp] for 0 <= cc - xp <= 20 (bank
+// conflict free: -15 * xp mod 32 is a permutation).  Features (B operand) are read as rows of 24 / 16 consecutive
+// pixels per channel.  Everything else (3xTF32 split, one MMA thread, commit barriers, register prefetch of the next
+// stage) is the forward's.  Epilogue: TMEM lanes = pixels, columns = channels -> 64-byte row segments per channel.
+constexpr int BK0 = 24, BK1 = 16;                    // K of the two stages of a neighbourhood row (36 -> 40 positions)
+constexpr int BA_FLOATS = UM * BK0;                  // A stage (sized for the larger half)
+constexpr int BB_FLOATS = 256 * BK0;                 // B stage
+constexpr int BSTAGE_FLOATS = 2 * (BA_FLOATS + BB_FLOATS);
+constexpr int BR_FLOATS = UTH * UD * UTW;            // 2688
+constexpr int BR_PER_THREAD = (BR_FLOATS + UTHREADS - 1) / UTHREADS;  // 11
+constexpr size_t BSMEM = sizeof(float) * (2 * BSTAGE_FLOATS + BR_FLOATS) + 1024;
+static_assert(BSMEM <= 227 * 1024, "backward stages do not fit");
+
+template <int DIR>
+__device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ feat, const float* __restrict__ gO,
+                                                   float* __restrict__ gI, const ofr::CorrGeom& g, int tiles_x,
+                                                   int tiles_y, int bid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* stages = reinterpret_cast<float*>(smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u));
+    float* Rs = stages + 2 * BSTAGE_FLOATS;
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int txi = bid % tiles_x;
+    bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int b = bid / tiles_y;
+    const int x0 = txi * UTW, y0 = tyi * UTH;
+    const int H = g.H, W = g.W, hw = H * W, C = g.C;
+    const uint32_t ncols = C <= 32 ? 32u : C <= 64 ? 64u : C <= 128 ? 128u : 256u;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+    const uint32_t LBO_A = UM * 16, LBO_B = (uint32_t)C * 16;
+
+    const float* fb = feat + (size_t)b * C * hw;
+    const float* gb = gO + (size_t)b * (UD * UD) * hw;
+
+    // gradient rows of neighbourhood row rr -> registers (11 elements of R per thread)
+    float pr[BR_PER_THREAD];
+    auto load_r = [&](int rr) {
+#pragma unroll
+        for (int i = 0; i < BR_PER_THREAD; ++i) {
+            const int idx = tid + UTHREADS * i;
+            const int xp = idx & 15, rest = idx >> 4, yp = rest / UD, dxx = rest - yp * UD;
+            const int dyy = rr - yp;
+            float v = 0.f;
+            if (idx < BR_FLOATS && (unsigned)dyy < (unsigned)UD) {
+                if (DIR == 0) {
+                    v = __ldg(gb + (size_t)(dyy * UD + dxx) * hw + (y0 + yp) * W + x0 + xp);
+                } else {
+                    const int yy = y0 - UR + rr, xx = x0 - UR + xp + dxx;
+                    if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W)
+                        v = __ldg(gb + (size_t)((UD - 1 - dyy) * UD + (UD - 1 - dxx)) * hw + yy * W + xx);
+                }
+            }
+            pr[i] = v;
+        }
+    };
+    // features of one stage -> registers: task = (channel c, 16-byte chunk kq) = 4 consecutive neighbourhood columns
+    float pb[6][4];
+    auto load_b = [&](int rr, int h) {
+        const int nk = h ? BK1 / 4 : BK0 / 4, cbase = h ? BK0 : 0;
+        const int yy = y0 - UR + rr;
+        const bool row_in = (unsigned)yy < (unsigned)H;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int t = tid + UTHREADS * i;
+            const int c = t / nk, kq = t - c * nk;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int cc = cbase + kq * 4 + e, xx = x0 - UR + cc;
+                const bool in = row_in && c < C && cc < UNW && (unsigned)xx < (unsigned)W;
+                pb[i][e] = in ? __ldg(fb + (size_t)c * hw + yy * W + xx) : 0.f;
+            }
+        }
+    };
+
+    const int nrows = UTH + 2 * UR;  // 28
+    load_r(0);
+    load_b(0, 0);
+    uint32_t it = 0;
+    for (int rr = 0; rr < nrows; ++rr) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h, ++it) {
+            const uint32_t buf = it & 1u;
+            const int kt = h ? BK1 : BK0, nk = kt / 4, cbase = h ? BK0 : 0;
+            float* sAh = stages + buf * BSTAGE_FLOATS;
+            float* sAl = sAh + BA_FLOATS;
+            float* sBh = sAl + BA_FLOATS;
+            float* sBl = sBh + BB_FLOATS;
+            if (it >= 2) mbar_wait_or_trap(&bars[buf], ((it >> 1) - 1u) & 1u);
+            if (h == 0) {
+                // (the previous row's A tiles were built before the last __syncthreads: R is free)
+#pragma unroll
+                for (int i = 0; i < BR_PER_THREAD; ++i) {
+                    const int idx = tid + UTHREADS * i;
+                    if (idx < BR_FLOATS) Rs[idx] = pr[i];
+                }
+                __syncthreads();
+            }
+            // A: task = (target t, chunk kq)
+            for (int t = tid; t < UM * nk; t += UTHREADS) {
+                const int m = t & (UM - 1), kq = t >> 7;
+                const int yp = m >> 4, xp = m & 15;
+                float4 hv, lv;
+                float* hp = &hv.x;
+                float* lp = &lv.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int dxx = cbase + kq * 4 + e - xp;
+                    const float v = (unsigned)dxx < (unsigned)UD ? Rs[(yp * UD + dxx) * UTW + xp] : 0.f;
+                    split_tf32(v, hp[e], lp[e]);
+                }
+                *reinterpret_cast<float4*>(sAh + kq * (UM * 4) + m * 4) = hv;
+                *reinterpret_cast<float4*>(sAl + kq * (UM * 4) + m * 4) = lv;
+            }
+            // B: the prefetched features
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int t = tid + UTHREADS * i;
+                const int c = t / nk, kq = t - c * nk;
+                if (c < C) {
+                    float4 hv, lv;
+                    split_tf32(pb[i][0], hv.x, lv.x);
+                    split_tf32(pb[i][1], hv.y, lv.y);
+                    split_tf32(pb[i][2], hv.z, lv.z);
+                    split_tf32(pb[i][3], hv.w, lv.w);
+                    *reinterpret_cast<float4*>(sBh + kq * (C * 4) + c * 4) = hv;
+                    *reinterpret_cast<float4*>(sBl + kq * (C * 4) + c * 4) = lv;
+                }
+            }
+            // next stage's loads: in flight during this stage's MMAs
+            if (h == 0) {
+                load_b(rr, 1);
+            } else if (rr + 1 < nrows) {
+                load_b(rr + 1, 0);
+                load_r(rr + 1);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int ks = 0; ks < kt / 8; ++ks) {
+                    const uint64_t dAh = umma_desc(s32(sAh) + ks * 2 * LBO_A, LBO_A), dAl = umma_desc(s32(sAl) + ks * 2 * LBO_A, LBO_A);
+                    const uint64_t dBh = umma_desc(s32(sBh) + ks * 2 * LBO_B, LBO_B), dBl = umma_desc(s32(sBl) + ks * 2 * LBO_B, LBO_B);
+                    umma_tf32(tmem_d, dAh, dBh, idesc, (it | (uint32_t)ks) ? 1u : 0u);
+                    umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
+                    umma_tf32(tmem_d, dAl, dBh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bars[buf]))
+                             : "memory");
+            }
+        }
+    }
+    mbar_wait_or_trap(&bars[(it - 1u) & 1u], ((it - 1u) >> 1) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+        const int yp = 2 * warp + (lane >> 4), xp = lane & 15;
+        const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+        float* o = gI + (size_t)b * C * hw + (y0 + yp) * W + x0 + xp;
+        for (int c0 = 0; c0 < C; c0 += 16) {
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(trow + c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) __stcs(o + (size_t)(c0 + j) * hw, __uint_as_float(v[j]) * g.scale);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+}
+
+// direction on the lowest bit of blockIdx.x: the two CTAs that read the same gradient planes are neighbours
+__global__ void __launch_bounds__(UTHREADS, 1) corr_bwd_umma_kernel(const float* __restrict__ f1,
+                                                                   const float* __restrict__ f2,
+                                                                   const float* __restrict__ gO, float* __restrict__ gI1,
+                                                                   float* __restrict__ gI2, ofr::CorrGeom g, int tiles_x,
+                                                                   int tiles_y, int ndir, int first) {
+    const int dir = (int)(blockIdx.x % ndir) + first;
+    if (dir == 0)
+        corr_bwd_umma_body<0>(f2, gO, gI1, g, tiles_x, tiles_y, blockIdx.x / ndir);
+    else
+        corr_bwd_umma_body<1>(f1, gO, gI2, g, tiles_x, tiles_y, blockIdx.x / ndir);
+}
+
 }  // namespace
 
 namespace ofr {
+
+static bool umma_enabled() {
+    static const bool enabled = [] {
+        const char* e = getenv("OFR_CORR_UMMA");
+        return !(e && e[0] == '0');
+    }();
+    return enabled;
+}
 
 // Class-image correlation (k = 1, s1 = s2 = 1, pad = md = 10) on the tensor cores.  OFR_ENOTSUP (nothing launched) when
 // the geometry does not tile (the caller then uses the FMA kernels).  OFR_CORR_UMMA=0 in the environment disables it
 // (A/B measurements only).
 int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
-    static const bool enabled = [] {
-        const char* e = getenv("OFR_CORR_UMMA");
-        return !(e && e[0] == '0');
-    }();
-    if (!enabled) return OFR_ENOTSUP;
+    if (!umma_enabled()) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % UKT) || g.C < UKT) return OFR_ENOTSUP;
     if ((long long)g.C * g.H * g.W >= (1ll << 30)) return OFR_ENOTSUP;
@@ -297,6 +517,24 @@ int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& 
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)USMEM));
     corr_fwd_umma_kernel<<<(unsigned)nblk, UTHREADS, USMEM, st>>>(f1, f2, out, g, tiles_x, tiles_y);
+    OFR_LAUNCH_CHECK();
+    return OFR_OK;
+}
+
+int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
+                  cudaStream_t st) {
+    if (!umma_enabled()) return OFR_ENOTSUP;
+    if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
+    if ((g.W % UTW) || (g.H % UTH) || (g.C % 16) || g.C < 16 || g.C > 256) return OFR_ENOTSUP;
+    if ((long long)g.C * g.H * g.W >= (1ll << 30) || (long long)UD * UD * g.H * g.W >= (1ll << 30)) return OFR_ENOTSUP;
+    const int ndir = (gI1 ? 1 : 0) + (gI2 ? 1 : 0);
+    if (ndir == 0) return OFR_OK;
+    const int tiles_x = g.W / UTW, tiles_y = g.H / UTH;
+    const long long nblk = (long long)tiles_x * tiles_y * g.B * ndir;
+    if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
+    OFR_CUDA(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSMEM));
+    corr_bwd_umma_kernel<<<(unsigned)nblk, UTHREADS, BSMEM, st>>>(f1, f2, gO, gI1, gI2, g, tiles_x, tiles_y, ndir,
+                                                                  gI1 ? 0 : 1);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
