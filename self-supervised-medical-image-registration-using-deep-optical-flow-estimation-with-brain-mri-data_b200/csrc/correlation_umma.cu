@@ -290,11 +290,13 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
 // pixels per channel.  Everything else (3xTF32 split, one MMA thread, commit barriers, register prefetch of the next
 // stage) is the forward's.  Epilogue: TMEM lanes = pixels, columns = channels -> 64-byte row segments per channel.
 constexpr int BK0 = 24, BK1 = 16;                    // K of the two stages of a neighbourhood row (36 -> 40 positions)
+constexpr int BTHREADS = 512;
 constexpr int BA_FLOATS = UM * BK0;                  // A stage (sized for the larger half)
-constexpr int BB_FLOATS = 256 * BK0;                 // B stage
+constexpr int BB_FLOATS = (256 + 1) * BK0;           // B stage (chunk stride padded by one row, see LBO_B)
 constexpr int BSTAGE_FLOATS = 2 * (BA_FLOATS + BB_FLOATS);
 constexpr int BR_FLOATS = UTH * UD * UTW;            // 2688
-constexpr int BR_PER_THREAD = (BR_FLOATS + UTHREADS - 1) / UTHREADS;  // 11
+constexpr int BR_PER_THREAD = (BR_FLOATS + BTHREADS - 1) / BTHREADS;  // 6
+constexpr int BB_TASKS = 256 * (BK0 / 4) / BTHREADS;                  // 3 feature tasks per thread and stage
 constexpr size_t BSMEM = sizeof(float) * (2 * BSTAGE_FLOATS + BR_FLOATS) + 1024;
 static_assert(BSMEM <= 227 * 1024, "backward stages do not fit");
 
@@ -332,57 +334,89 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-    const uint32_t LBO_A = UM * 16, LBO_B = (uint32_t)C * 16;
+    // B chunks are (C + 1) rows apart: a warp stores the 6 (4) chunks of ~5 (8) consecutive channels at once, and with a
+    // stride of exactly C rows all chunks of a channel fall on the same four banks (6-way conflict on every store)
+    const uint32_t LBO_A = UM * 16, LBO_B = (uint32_t)(C + 1) * 16;
 
     const float* fb = feat + (size_t)b * C * hw;
     const float* gb = gO + (size_t)b * (UD * UD) * hw;
 
-    // gradient rows of neighbourhood row rr -> registers (11 elements of R per thread)
+    // ---- per-thread constants of the staging tasks (everything that does not depend on the neighbourhood row) ----
+    // R: element idx = (yp * 21 + dxx) * 16 + xp of the gradient buffer of a row
+    int r_off[BR_PER_THREAD], r_yp[BR_PER_THREAD];  // r_off < 0: never loaded
+#pragma unroll
+    for (int i = 0; i < BR_PER_THREAD; ++i) {
+        const int idx = tid + BTHREADS * i;
+        const int xp = idx & 15, rest = idx >> 4, yp = rest / UD, dxx = rest - yp * UD;
+        r_yp[i] = yp;
+        if (idx >= BR_FLOATS) {
+            r_off[i] = -1;
+        } else if (DIR == 0) {  // gO[(dyy * 21 + dxx)][y0 + yp][x0 + xp]
+            r_off[i] = dxx * hw + (y0 + yp) * W + x0 + xp;
+        } else {                // gO[(20 - dyy) * 21 + 20 - dxx][y0 - 10 + rr][x0 - 10 + xp + dxx]
+            const int xx = x0 - UR + xp + dxx;
+            r_off[i] = (unsigned)xx < (unsigned)W ? (UD - 1 - dxx) * hw + xx : -1;
+        }
+    }
+    // B: task = (channel c, chunk kq of 4 neighbourhood columns); per half h its own decomposition
+    int b_off[2][BB_TASKS], b_dst[2][BB_TASKS];
+    unsigned b_msk[2][BB_TASKS];  // bit e: column of element e is inside the image (and the task exists)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int nk = h ? BK1 / 4 : BK0 / 4, cbase = h ? BK0 : 0;
+#pragma unroll
+        for (int i = 0; i < BB_TASKS; ++i) {
+            const int t = tid + BTHREADS * i;
+            const int c = t / nk, kq = t - c * nk;
+            const int xx0 = x0 - UR + cbase + kq * 4;
+            unsigned m = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c < C && cbase + kq * 4 + e < UNW && (unsigned)(xx0 + e) < (unsigned)W) m |= 1u << e;
+            b_msk[h][i] = m;
+            b_off[h][i] = c * hw + xx0;
+            b_dst[h][i] = kq * ((C + 1) * 4) + c * 4;
+        }
+    }
+
     float pr[BR_PER_THREAD];
     auto load_r = [&](int rr) {
 #pragma unroll
         for (int i = 0; i < BR_PER_THREAD; ++i) {
-            const int idx = tid + UTHREADS * i;
-            const int xp = idx & 15, rest = idx >> 4, yp = rest / UD, dxx = rest - yp * UD;
-            const int dyy = rr - yp;
+            const int dyy = rr - r_yp[i];
             float v = 0.f;
-            if (idx < BR_FLOATS && (unsigned)dyy < (unsigned)UD) {
+            if (r_off[i] >= 0 && (unsigned)dyy < (unsigned)UD) {
                 if (DIR == 0) {
-                    v = __ldg(gb + (size_t)(dyy * UD + dxx) * hw + (y0 + yp) * W + x0 + xp);
+                    v = __ldg(gb + (size_t)(dyy * UD) * hw + r_off[i]);
                 } else {
-                    const int yy = y0 - UR + rr, xx = x0 - UR + xp + dxx;
-                    if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W)
-                        v = __ldg(gb + (size_t)((UD - 1 - dyy) * UD + (UD - 1 - dxx)) * hw + yy * W + xx);
+                    const int yy = y0 - UR + rr;
+                    if ((unsigned)yy < (unsigned)H) v = __ldg(gb + (size_t)((UD - 1 - dyy) * UD) * hw + yy * W + r_off[i]);
                 }
             }
             pr[i] = v;
         }
     };
-    // features of one stage -> registers: task = (channel c, 16-byte chunk kq) = 4 consecutive neighbourhood columns
-    float pb[6][4];
-    auto load_b = [&](int rr, int h) {
-        const int nk = h ? BK1 / 4 : BK0 / 4, cbase = h ? BK0 : 0;
+    float pb[2][BB_TASKS][4];  // set h holds the features of stage (row, h)
+    auto load_b = [&](int rr, int h, float (&dst)[BB_TASKS][4]) {
         const int yy = y0 - UR + rr;
         const bool row_in = (unsigned)yy < (unsigned)H;
+        const float* rowp = fb + yy * W;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int t = tid + UTHREADS * i;
-            const int c = t / nk, kq = t - c * nk;
+        for (int i = 0; i < BB_TASKS; ++i) {
+            const unsigned m = row_in ? b_msk[h][i] : 0u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int cc = cbase + kq * 4 + e, xx = x0 - UR + cc;
-                const bool in = row_in && c < C && cc < UNW && (unsigned)xx < (unsigned)W;
-                pb[i][e] = in ? __ldg(fb + (size_t)c * hw + yy * W + xx) : 0.f;
-            }
+            for (int e = 0; e < 4; ++e) dst[i][e] = (m >> e) & 1u ? __ldg(rowp + b_off[h][i] + e) : 0.f;
         }
     };
 
     const int nrows = UTH + 2 * UR;  // 28
     load_r(0);
-    load_b(0, 0);
+    load_b(0, 0, pb[0]);
+    load_b(0, 1, pb[1]);
     uint32_t it = 0;
-    for (int rr = 0; rr < nrows; ++rr) {
 #pragma unroll 1
+    for (int rr = 0; rr < nrows; ++rr) {
+#pragma unroll
         for (int h = 0; h < 2; ++h, ++it) {
             const uint32_t buf = it & 1u;
             const int kt = h ? BK1 : BK0, nk = kt / 4, cbase = h ? BK0 : 0;
@@ -395,53 +429,45 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
                 // (the previous row's A tiles were built before the last __syncthreads: R is free)
 #pragma unroll
                 for (int i = 0; i < BR_PER_THREAD; ++i) {
-                    const int idx = tid + UTHREADS * i;
+                    const int idx = tid + BTHREADS * i;
                     if (idx < BR_FLOATS) Rs[idx] = pr[i];
                 }
                 __syncthreads();
+                if (rr + 1 < nrows) load_r(rr + 1);  // two stages ahead of its use
             }
-            // A: task = (target t, chunk kq)
-            for (int t = tid; t < UM * nk; t += UTHREADS) {
+            // A: task = (target t, chunk kq): 128 * nk tasks
+            for (int t = tid; t < UM * nk; t += BTHREADS) {
                 const int m = t & (UM - 1), kq = t >> 7;
                 const int yp = m >> 4, xp = m & 15;
+                const float* rp = Rs + yp * (UD * UTW) + xp;
+                const int d0 = cbase + kq * 4 - xp;
                 float4 hv, lv;
-                float* hp = &hv.x;
-                float* lp = &lv.x;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int dxx = cbase + kq * 4 + e - xp;
-                    const float v = (unsigned)dxx < (unsigned)UD ? Rs[(yp * UD + dxx) * UTW + xp] : 0.f;
-                    split_tf32(v, hp[e], lp[e]);
-                }
+                split_tf32((unsigned)(d0 + 0) < (unsigned)UD ? rp[(d0 + 0) * UTW] : 0.f, hv.x, lv.x);
+                split_tf32((unsigned)(d0 + 1) < (unsigned)UD ? rp[(d0 + 1) * UTW] : 0.f, hv.y, lv.y);
+                split_tf32((unsigned)(d0 + 2) < (unsigned)UD ? rp[(d0 + 2) * UTW] : 0.f, hv.z, lv.z);
+                split_tf32((unsigned)(d0 + 3) < (unsigned)UD ? rp[(d0 + 3) * UTW] : 0.f, hv.w, lv.w);
                 *reinterpret_cast<float4*>(sAh + kq * (UM * 4) + m * 4) = hv;
                 *reinterpret_cast<float4*>(sAl + kq * (UM * 4) + m * 4) = lv;
             }
-            // B: the prefetched features
+            // B: the prefetched features of this stage
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const int t = tid + UTHREADS * i;
-                const int c = t / nk, kq = t - c * nk;
-                if (c < C) {
+            for (int i = 0; i < BB_TASKS; ++i) {
+                if (b_msk[h][i] || (tid + BTHREADS * i) / nk < C) {
                     float4 hv, lv;
-                    split_tf32(pb[i][0], hv.x, lv.x);
-                    split_tf32(pb[i][1], hv.y, lv.y);
-                    split_tf32(pb[i][2], hv.z, lv.z);
-                    split_tf32(pb[i][3], hv.w, lv.w);
-                    *reinterpret_cast<float4*>(sBh + kq * (C * 4) + c * 4) = hv;
-                    *reinterpret_cast<float4*>(sBl + kq * (C * 4) + c * 4) = lv;
+                    split_tf32(pb[h][i][0], hv.x, lv.x);
+                    split_tf32(pb[h][i][1], hv.y, lv.y);
+                    split_tf32(pb[h][i][2], hv.z, lv.z);
+                    split_tf32(pb[h][i][3], hv.w, lv.w);
+                    *reinterpret_cast<float4*>(sBh + b_dst[h][i]) = hv;
+                    *reinterpret_cast<float4*>(sBl + b_dst[h][i]) = lv;
                 }
             }
-            // next stage's loads: in flight during this stage's MMAs
-            if (h == 0) {
-                load_b(rr, 1);
-            } else if (rr + 1 < nrows) {
-                load_b(rr + 1, 0);
-                load_r(rr + 1);
-            }
+            if (rr + 1 < nrows) load_b(rr + 1, h, pb[h]);  // the same half of the next row: two stages ahead
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
                 for (int ks = 0; ks < kt / 8; ++ks) {
                     const uint64_t dAh = umma_desc(s32(sAh) + ks * 2 * LBO_A, LBO_A), dAl = umma_desc(s32(sAl) + ks * 2 * LBO_A, LBO_A);
                     const uint64_t dBh = umma_desc(s32(sBh) + ks * 2 * LBO_B, LBO_B), dBl = umma_desc(s32(sBl) + ks * 2 * LBO_B, LBO_B);
@@ -480,7 +506,7 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
 }
 
 // direction on the lowest bit of blockIdx.x: the two CTAs that read the same gradient planes are neighbours
-__global__ void __launch_bounds__(UTHREADS, 1) corr_bwd_umma_kernel(const float* __restrict__ f1,
+__global__ void __launch_bounds__(BTHREADS, 1) corr_bwd_umma_kernel(const float* __restrict__ f1,
                                                                    const float* __restrict__ f2,
                                                                    const float* __restrict__ gO, float* __restrict__ gI1,
                                                                    float* __restrict__ gI2, ofr::CorrGeom g, int tiles_x,
@@ -533,7 +559,7 @@ int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1,
     const long long nblk = (long long)tiles_x * tiles_y * g.B * ndir;
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSMEM));
-    corr_bwd_umma_kernel<<<(unsigned)nblk, UTHREADS, BSMEM, st>>>(f1, f2, gO, gI1, gI2, g, tiles_x, tiles_y, ndir,
+    corr_bwd_umma_kernel<<<(unsigned)nblk, BTHREADS, BSMEM, st>>>(f1, f2, gO, gI1, gI2, g, tiles_x, tiles_y, ndir,
                                                                   gI1 ? 0 : 1);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
