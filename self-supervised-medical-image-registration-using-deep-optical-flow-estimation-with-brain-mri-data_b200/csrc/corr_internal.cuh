@@ -26,8 +26,10 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
 
 // tcgen05 / TMEM forward for the class-image problem of the FlowNetC window (pad = md = 10 after the polyphase split):
 // correlation_umma.cu.  OFR_ENOTSUP when the geometry does not tile.
-int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st);
+// `g` is the class geometry (B*4 class images of H/2 x W/2).  full_src: the inputs (f1, f2, gO) are the operator's own
+// [B][C][H][W] tensors and are read in place with stride 2; the outputs are always written in the class layout.
+int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src = false);
 int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
-                  cudaStream_t st);
+                  cudaStream_t st, bool full_src = false);
 
 }  // namespace ofr

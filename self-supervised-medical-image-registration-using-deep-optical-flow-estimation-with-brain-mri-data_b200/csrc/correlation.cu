@@ -421,7 +421,11 @@ extern "C" int ofr_corr_fwd_act(const float* f1, const float* f2, float* out, in
         float* f2p = (float*)((char*)ws + feat);
         float* outp = (float*)((char*)ws + 2 * feat);
         const CorrGeom cg = class_geom(g);
-        int rc = polyphase(true, f1, f1p, B, C, H, W, st);
+        // tensor-core kernel: reads f1 / f2 in place (stride 2), no split pass
+        int rc = ofr::corr_fwd_umma(f1, f2, outp, cg, st, true);
+        if (rc == OFR_OK) return polyphase(false, outp, out, B, g.D * g.D, H, W, st);
+        if (rc != OFR_ENOTSUP) return rc;
+        rc = polyphase(true, f1, f1p, B, C, H, W, st);
         if (rc == OFR_OK) rc = polyphase(true, f2, f2p, B, C, H, W, st);
         if (rc != OFR_OK) return rc;
         rc = ofr::corr_fwd_tma(f1p, f2p, outp, cg, st);
@@ -468,7 +472,15 @@ extern "C" int ofr_corr_bwd(const float* f1, const float* f2, const float* gO, f
         float* g1p = (float*)(w + 2 * feat + vol);
         float* g2p = (float*)(w + 3 * feat + vol);
         const CorrGeom cg = class_geom(g);
-        int rc = OFR_OK;
+        // tensor-core kernel: reads f1 / f2 / gO in place (stride 2), no split passes
+        int rc = ofr::corr_bwd_umma(f1, f2, gO, gI1 ? g1p : nullptr, gI2 ? g2p : nullptr, cg, st, true);
+        if (rc == OFR_OK) {
+            if (gI1) rc = polyphase(false, g1p, gI1, B, C, H, W, st);
+            if (rc == OFR_OK && gI2) rc = polyphase(false, g2p, gI2, B, C, H, W, st);
+            return rc;
+        }
+        if (rc != OFR_ENOTSUP) return rc;
+        rc = OFR_OK;
         if (gI2) rc = polyphase(true, f1, f1p, B, C, H, W, st);
         if (rc == OFR_OK && gI1) rc = polyphase(true, f2, f2p, B, C, H, W, st);
         if (rc == OFR_OK) rc = polyphase(true, gO, gOp, B, g.D * g.D, H, W, st);

@@ -45,6 +45,30 @@ constexpr int EBUF_FLOATS = 4 * UD * 32;
 constexpr size_t USMEM = sizeof(float) * (2 * STAGE_FLOATS + EBUF_FLOATS) + 1024;
 static_assert(UCHUNKS * UROWS == UTH + 2 * UR && UROWS * UNW <= UN, "chunking");
 
+// Where the class images live.  full = 0: class layout [B*4][C][H][W] (the polyphase split has been run).  full = 1: the
+// operator's own tensors [B][C][2H][2W]; class q = 2*py + px of image b is read in place with stride 2 (pixel (y, x) of
+// the class image is (2y + py, 2x + px)), so no split pass and no second copy of the inputs exists.  The four classes
+// of an image are neighbours in launch order: the half-used sectors of one class are L2 hits for the next.
+struct SrcMap {
+    int full;
+};
+struct SrcView {
+    size_t base;   // element offset of (channel 0, pixel (0,0)) of this class image
+    int cs, rs, xs;  // channel / row / column strides in elements
+};
+__device__ __forceinline__ SrcView src_view(const SrcMap& m, int b4, int planes, int H, int W) {
+    SrcView v;
+    if (m.full) {
+        const int b = b4 >> 2, py = (b4 >> 1) & 1, px = b4 & 1;
+        v.cs = 4 * H * W, v.rs = 4 * W, v.xs = 2;
+        v.base = (size_t)b * planes * v.cs + py * 2 * W + px;
+    } else {
+        v.cs = H * W, v.rs = W, v.xs = 1;
+        v.base = (size_t)b4 * planes * v.cs;
+    }
+    return v;
+}
+
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // shared-memory matrix descriptor, K-major, no swizzle: element (row r, 16-byte chunk j along K) at j * LBO + r * 16
@@ -99,7 +123,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float* __restrict__ f1,
                                                                    const float* __restrict__ f2,
                                                                    float* __restrict__ out, ofr::CorrGeom g,
-                                                                   int tiles_x, int tiles_y) {
+                                                                   int tiles_x, int tiles_y, SrcMap sm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u));
     float* ebuf = stages + 2 * STAGE_FLOATS;
@@ -137,13 +161,15 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
 
     // staging tasks: one task = one row of an operand (a pixel) x 4 consecutive channels = one 16-byte chunk
     //   A: 128 pixels x 4 chunks = 512 tasks (2 per thread);  B: 256 positions x 4 chunks = 1024 tasks (4 per thread)
-    const float* f1b = f1 + (size_t)b * C * hw;
-    const float* f2b = f2 + (size_t)b * C * hw;
+    const SrcView sv = src_view(sm, b, C, H, W);
+    const int cs = sv.cs;
+    const float* f1b = f1 + sv.base;
+    const float* f2b = f2 + sv.base;
     int a_src[2], a_dst[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int t = tid + UTHREADS * i, m = t & (UM - 1), kq = t >> 7;
-        a_src[i] = kq * 4 * hw + (y0 + (m >> 4)) * W + x0 + (m & 15);
+        a_src[i] = kq * 4 * cs + (y0 + (m >> 4)) * sv.rs + (x0 + (m & 15)) * sv.xs;
         a_dst[i] = kq * (UM * 4) + m * 4;
     }
     int b_dst[4];
@@ -163,20 +189,20 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
             const int rc = j / UNW, cc = j - rc * UNW;
             const int yy = y0 - UR + n * UROWS + rc, xx = x0 - UR + cc;
             const bool in = j < UROWS * UNW && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
-            b_src[i] = in ? kq * 4 * hw + yy * W + xx : -1;
+            b_src[i] = in ? kq * 4 * cs + yy * sv.rs + xx * sv.xs : -1;
         }
         float pa[2][4], pb[4][4];
         auto load = [&](int s) {
-            const float* p1 = f1b + (size_t)s * UKT * hw;
-            const float* p2 = f2b + (size_t)s * UKT * hw;
+            const float* p1 = f1b + (size_t)s * UKT * cs;
+            const float* p2 = f2b + (size_t)s * UKT * cs;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) pa[i][c] = __ldg(p1 + a_src[i] + c * hw);
+                for (int c = 0; c < 4; ++c) pa[i][c] = __ldg(p1 + a_src[i] + c * cs);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) pb[i][c] = b_src[i] >= 0 ? __ldg(p2 + b_src[i] + c * hw) : 0.f;
+                for (int c = 0; c < 4; ++c) pb[i][c] = b_src[i] >= 0 ? __ldg(p2 + b_src[i] + c * cs) : 0.f;
         };
         load(0);
         for (int s = 0; s < nstages; ++s, ++it) {
@@ -303,7 +329,7 @@ static_assert(BSMEM <= 227 * 1024, "backward stages do not fit");
 template <int DIR>
 __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ feat, const float* __restrict__ gO,
                                                    float* __restrict__ gI, const ofr::CorrGeom& g, int tiles_x,
-                                                   int tiles_y, int bid) {
+                                                   int tiles_y, int bid, const SrcMap& sm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u));
     float* Rs = stages + 2 * BSTAGE_FLOATS;
@@ -338,8 +364,9 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
     // stride of exactly C rows all chunks of a channel fall on the same four banks (6-way conflict on every store)
     const uint32_t LBO_A = UM * 16, LBO_B = (uint32_t)(C + 1) * 16;
 
-    const float* fb = feat + (size_t)b * C * hw;
-    const float* gb = gO + (size_t)b * (UD * UD) * hw;
+    const SrcView fv = src_view(sm, b, C, H, W), gv = src_view(sm, b, UD * UD, H, W);
+    const float* fb = feat + fv.base;
+    const float* gb = gO + gv.base;
 
     // ---- per-thread constants of the staging tasks (everything that does not depend on the neighbourhood row) ----
     // R: element idx = (yp * 21 + dxx) * 16 + xp of the gradient buffer of a row
@@ -352,10 +379,10 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
         if (idx >= BR_FLOATS) {
             r_off[i] = -1;
         } else if (DIR == 0) {  // gO[(dyy * 21 + dxx)][y0 + yp][x0 + xp]
-            r_off[i] = dxx * hw + (y0 + yp) * W + x0 + xp;
+            r_off[i] = dxx * gv.cs + (y0 + yp) * gv.rs + (x0 + xp) * gv.xs;
         } else {                // gO[(20 - dyy) * 21 + 20 - dxx][y0 - 10 + rr][x0 - 10 + xp + dxx]
             const int xx = x0 - UR + xp + dxx;
-            r_off[i] = (unsigned)xx < (unsigned)W ? (UD - 1 - dxx) * hw + xx : -1;
+            r_off[i] = (unsigned)xx < (unsigned)W ? (UD - 1 - dxx) * gv.cs + xx * gv.xs : -1;
         }
     }
     // B: task = (channel c, chunk kq of 4 neighbourhood columns); per half h its own decomposition
@@ -374,7 +401,7 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
             for (int e = 0; e < 4; ++e)
                 if (c < C && cbase + kq * 4 + e < UNW && (unsigned)(xx0 + e) < (unsigned)W) m |= 1u << e;
             b_msk[h][i] = m;
-            b_off[h][i] = c * hw + xx0;
+            b_off[h][i] = c * fv.cs + xx0 * fv.xs;
             b_dst[h][i] = kq * ((C + 1) * 4) + c * 4;
         }
     }
@@ -387,10 +414,11 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
             float v = 0.f;
             if (r_off[i] >= 0 && (unsigned)dyy < (unsigned)UD) {
                 if (DIR == 0) {
-                    v = __ldg(gb + (size_t)(dyy * UD) * hw + r_off[i]);
+                    v = __ldg(gb + (size_t)(dyy * UD) * gv.cs + r_off[i]);
                 } else {
                     const int yy = y0 - UR + rr;
-                    if ((unsigned)yy < (unsigned)H) v = __ldg(gb + (size_t)((UD - 1 - dyy) * UD) * hw + yy * W + r_off[i]);
+                    if ((unsigned)yy < (unsigned)H)
+                        v = __ldg(gb + (size_t)((UD - 1 - dyy) * UD) * gv.cs + yy * gv.rs + r_off[i]);
                 }
             }
             pr[i] = v;
@@ -400,12 +428,12 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
     auto load_b = [&](int rr, int h, float (&dst)[BB_TASKS][4]) {
         const int yy = y0 - UR + rr;
         const bool row_in = (unsigned)yy < (unsigned)H;
-        const float* rowp = fb + yy * W;
+        const float* rowp = fb + yy * fv.rs;
 #pragma unroll
         for (int i = 0; i < BB_TASKS; ++i) {
             const unsigned m = row_in ? b_msk[h][i] : 0u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dst[i][e] = (m >> e) & 1u ? __ldg(rowp + b_off[h][i] + e) : 0.f;
+            for (int e = 0; e < 4; ++e) dst[i][e] = (m >> e) & 1u ? __ldg(rowp + b_off[h][i] + e * fv.xs) : 0.f;
         }
     };
 
@@ -510,12 +538,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) corr_bwd_umma_kernel(const float*
                                                                    const float* __restrict__ f2,
                                                                    const float* __restrict__ gO, float* __restrict__ gI1,
                                                                    float* __restrict__ gI2, ofr::CorrGeom g, int tiles_x,
-                                                                   int tiles_y, int ndir, int first) {
+                                                                   int tiles_y, int ndir, int first, SrcMap sm) {
     const int dir = (int)(blockIdx.x % ndir) + first;
     if (dir == 0)
-        corr_bwd_umma_body<0>(f2, gO, gI1, g, tiles_x, tiles_y, blockIdx.x / ndir);
+        corr_bwd_umma_body<0>(f2, gO, gI1, g, tiles_x, tiles_y, blockIdx.x / ndir, sm);
     else
-        corr_bwd_umma_body<1>(f1, gO, gI2, g, tiles_x, tiles_y, blockIdx.x / ndir);
+        corr_bwd_umma_body<1>(f1, gO, gI2, g, tiles_x, tiles_y, blockIdx.x / ndir, sm);
 }
 
 }  // namespace
@@ -533,7 +561,7 @@ static bool umma_enabled() {
 // Class-image correlation (k = 1, s1 = s2 = 1, pad = md = 10) on the tensor cores.  OFR_ENOTSUP (nothing launched) when
 // the geometry does not tile (the caller then uses the FMA kernels).  OFR_CORR_UMMA=0 in the environment disables it
 // (A/B measurements only).
-int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st) {
+int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src) {
     if (!umma_enabled()) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % UKT) || g.C < UKT) return OFR_ENOTSUP;
@@ -542,17 +570,18 @@ int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& 
     const long long nblk = (long long)tiles_x * tiles_y * g.B;
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)USMEM));
-    corr_fwd_umma_kernel<<<(unsigned)nblk, UTHREADS, USMEM, st>>>(f1, f2, out, g, tiles_x, tiles_y);
+    if ((long long)g.C * g.H * g.W * 4 >= (1ll << 30)) return OFR_ENOTSUP;
+    corr_fwd_umma_kernel<<<(unsigned)nblk, UTHREADS, USMEM, st>>>(f1, f2, out, g, tiles_x, tiles_y, SrcMap{full_src ? 1 : 0});
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
 
 int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool full_src) {
     if (!umma_enabled()) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % 16) || g.C < 16 || g.C > 256) return OFR_ENOTSUP;
-    if ((long long)g.C * g.H * g.W >= (1ll << 30) || (long long)UD * UD * g.H * g.W >= (1ll << 30)) return OFR_ENOTSUP;
+    if ((long long)g.C * g.H * g.W * 4 >= (1ll << 30) || (long long)UD * UD * g.H * g.W * 4 >= (1ll << 30)) return OFR_ENOTSUP;
     const int ndir = (gI1 ? 1 : 0) + (gI2 ? 1 : 0);
     if (ndir == 0) return OFR_OK;
     const int tiles_x = g.W / UTW, tiles_y = g.H / UTH;
@@ -560,7 +589,7 @@ int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1,
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSMEM));
     corr_bwd_umma_kernel<<<(unsigned)nblk, BTHREADS, BSMEM, st>>>(f1, f2, gO, gI1, gI2, g, tiles_x, tiles_y, ndir,
-                                                                  gI1 ? 0 : 1);
+                                                                  gI1 ? 0 : 1, SrcMap{full_src ? 1 : 0});
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
