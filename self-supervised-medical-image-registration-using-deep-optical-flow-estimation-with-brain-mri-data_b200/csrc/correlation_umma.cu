@@ -182,6 +182,9 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
     const int nstages = C / UKT;
     uint32_t it = 0;  // stages issued so far (buffer = it & 1)
     for (int n = 0; n < UCHUNKS; ++n) {
+        // a chunk whose 7 neighbourhood rows all lie outside the image is all zero padding: no GEMM, the epilogue
+        // writes the zeros (top / bottom tiles: 2 of the 16 chunks of a 32-row class image)
+        const bool chunk_live = y0 - UR + n * UROWS + UROWS > 0 && y0 - UR + n * UROWS < H;
         int b_src[4];  // element offset of the task's neighbour inside one channel plane, or -1 (zero padding)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -204,8 +207,8 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
 #pragma unroll
                 for (int c = 0; c < 4; ++c) pb[i][c] = b_src[i] >= 0 ? __ldg(p2 + b_src[i] + c * cs) : 0.f;
         };
-        load(0);
-        for (int s = 0; s < nstages; ++s, ++it) {
+        if (chunk_live) load(0);
+        for (int s = 0; chunk_live && s < nstages; ++s, ++it) {
             const uint32_t buf = it & 1u;
             float* sAh = stages + buf * STAGE_FLOATS;
             float* sAl = sAh + A_FLOATS;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
             }
         }
         // the chunk's accumulators are complete when the last stage's commit has arrived
-        mbar_wait_or_trap(&bars[(it - 1u) & 1u], ((it - 1u) >> 1) & 1u);
+        if (chunk_live) mbar_wait_or_trap(&bars[(it - 1u) & 1u], ((it - 1u) >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (warp < 4) {
             const int yp = 2 * warp + (lane >> 4), xp = lane & 15;
@@ -263,6 +266,14 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
                 const bool valid = (unsigned)dy < (unsigned)UD;
                 uint32_t v[UNW];
                 const uint32_t ta = trow + rc * UNW;
+                if (!chunk_live) {  // (CTA-uniform)
+                    if (valid) {
+                        float* o = out + (((size_t)b * (UD * UD) + dy * UD) * H + y0 + yp) * W + x0 + xp;
+#pragma unroll
+                        for (int dx = 0; dx < UD; ++dx) __stcs(o + (size_t)dx * hw, 0.f);
+                    }
+                    continue;
+                }
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -437,13 +448,15 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
         }
     };
 
-    const int nrows = UTH + 2 * UR;  // 28
-    load_r(0);
-    load_b(0, 0, pb[0]);
-    load_b(0, 1, pb[1]);
+    // neighbourhood rows outside the image multiply zero features (gI1) / zero gradients (gI2): only the rows inside
+    // are walked (18 of the 28 for the top and bottom tiles of a 32-row class image)
+    const int r_lo = max(0, UR - y0), nrows = min(UTH + 2 * UR, H + UR - y0);
+    load_r(r_lo);
+    load_b(r_lo, 0, pb[0]);
+    load_b(r_lo, 1, pb[1]);
     uint32_t it = 0;
 #pragma unroll 1
-    for (int rr = 0; rr < nrows; ++rr) {
+    for (int rr = r_lo; rr < nrows; ++rr) {
 #pragma unroll
         for (int h = 0; h < 2; ++h, ++it) {
             const uint32_t buf = it & 1u;
