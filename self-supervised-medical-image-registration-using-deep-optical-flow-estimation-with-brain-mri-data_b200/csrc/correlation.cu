@@ -422,8 +422,7 @@ extern "C" int ofr_corr_fwd_act(const float* f1, const float* f2, float* out, in
         float* outp = (float*)((char*)ws + 2 * feat);
         const CorrGeom cg = class_geom(g);
         // tensor-core kernel: reads f1 / f2 in place (stride 2), no split pass
-        int rc = ofr::corr_fwd_umma(f1, f2, outp, cg, st, true);
-        if (rc == OFR_OK) return polyphase(false, outp, out, B, g.D * g.D, H, W, st);
+        int rc = ofr::corr_fwd_umma(f1, f2, out, cg, st, true, true);
         if (rc != OFR_ENOTSUP) return rc;
         rc = polyphase(true, f1, f1p, B, C, H, W, st);
         if (rc == OFR_OK) rc = polyphase(true, f2, f2p, B, C, H, W, st);

@@ -50,7 +50,8 @@ static_assert(UCHUNKS * UROWS == UTH + 2 * UR && UROWS * UNW <= UN, "chunking");
 // the class image is (2y + py, 2x + px)), so no split pass and no second copy of the inputs exists.  The four classes
 // of an image are neighbours in launch order: the half-used sectors of one class are L2 hits for the next.
 struct SrcMap {
-    int full;
+    int full;      // inputs in place (stride 2)
+    int dst_full;  // outputs written in place too (no merge pass)
 };
 struct SrcView {
     size_t base;   // element offset of (channel 0, pixel (0,0)) of this class image
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
     // staging tasks: one task = one row of an operand (a pixel) x 4 consecutive channels = one 16-byte chunk
     //   A: 128 pixels x 4 chunks = 512 tasks (2 per thread);  B: 256 positions x 4 chunks = 1024 tasks (4 per thread)
     const SrcView sv = src_view(sm, b, C, H, W);
+    const SrcView dv = src_view(SrcMap{sm.dst_full, 0}, b, UD * UD, H, W);
     const int cs = sv.cs;
     const float* f1b = f1 + sv.base;
     const float* f2b = f2 + sv.base;
@@ -268,9 +270,9 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
                 const uint32_t ta = trow + rc * UNW;
                 if (!chunk_live) {  // (CTA-uniform)
                     if (valid) {
-                        float* o = out + (((size_t)b * (UD * UD) + dy * UD) * H + y0 + yp) * W + x0 + xp;
+                        float* o = out + dv.base + (size_t)(dy * UD) * dv.cs + (y0 + yp) * dv.rs + (x0 + xp) * dv.xs;
 #pragma unroll
-                        for (int dx = 0; dx < UD; ++dx) __stcs(o + (size_t)dx * hw, 0.f);
+                        for (int dx = 0; dx < UD; ++dx) __stcs(o + (size_t)dx * dv.cs, 0.f);
                     }
                     continue;
                 }
@@ -297,9 +299,9 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
                 }
                 __syncwarp();
                 if (valid) {
-                    float* o = out + (((size_t)b * (UD * UD) + dy * UD) * H + y0 + yp) * W + x0 + xp;
+                    float* o = out + dv.base + (size_t)(dy * UD) * dv.cs + (y0 + yp) * dv.rs + (x0 + xp) * dv.xs;
 #pragma unroll
-                    for (int dx = 0; dx < UD; ++dx) __stcs(o + (size_t)dx * hw, eb[dx * 32 + lane]);
+                    for (int dx = 0; dx < UD; ++dx) __stcs(o + (size_t)dx * dv.cs, eb[dx * 32 + lane]);
                 }
                 __syncwarp();
             }
@@ -574,7 +576,8 @@ static bool umma_enabled() {
 // Class-image correlation (k = 1, s1 = s2 = 1, pad = md = 10) on the tensor cores.  OFR_ENOTSUP (nothing launched) when
 // the geometry does not tile (the caller then uses the FMA kernels).  OFR_CORR_UMMA=0 in the environment disables it
 // (A/B measurements only).
-int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src) {
+int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src,
+                  bool full_dst) {
     if (!umma_enabled()) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % UKT) || g.C < UKT) return OFR_ENOTSUP;
@@ -584,7 +587,7 @@ int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& 
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)USMEM));
     if ((long long)g.C * g.H * g.W * 4 >= (1ll << 30)) return OFR_ENOTSUP;
-    corr_fwd_umma_kernel<<<(unsigned)nblk, UTHREADS, USMEM, st>>>(f1, f2, out, g, tiles_x, tiles_y, SrcMap{full_src ? 1 : 0});
+    corr_fwd_umma_kernel<<<(unsigned)nblk, UTHREADS, USMEM, st>>>(f1, f2, out, g, tiles_x, tiles_y, SrcMap{full_src ? 1 : 0, full_dst ? 1 : 0});
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
@@ -602,7 +605,7 @@ int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1,
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSMEM));
     corr_bwd_umma_kernel<<<(unsigned)nblk, BTHREADS, BSMEM, st>>>(f1, f2, gO, gI1, gI2, g, tiles_x, tiles_y, ndir,
-                                                                  gI1 ? 0 : 1, SrcMap{full_src ? 1 : 0});
+                                                                  gI1 ? 0 : 1, SrcMap{full_src ? 1 : 0, 0});
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
