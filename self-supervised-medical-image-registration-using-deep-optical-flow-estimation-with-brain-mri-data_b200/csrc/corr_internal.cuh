@@ -31,6 +31,6 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
 int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src = false,
                   bool full_dst = false);  // full_dst: `out` is the operator's own [B][D*D][H][W] tensor (no merge pass)
 int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
-                  cudaStream_t st, bool full_src = false);
+                  cudaStream_t st, bool full_src = false, bool full_dst = false);
 
 }  // namespace ofr

@@ -472,12 +472,7 @@ extern "C" int ofr_corr_bwd(const float* f1, const float* f2, const float* gO, f
         float* g2p = (float*)(w + 3 * feat + vol);
         const CorrGeom cg = class_geom(g);
         // tensor-core kernel: reads f1 / f2 / gO in place (stride 2), no split passes
-        int rc = ofr::corr_bwd_umma(f1, f2, gO, gI1 ? g1p : nullptr, gI2 ? g2p : nullptr, cg, st, true);
-        if (rc == OFR_OK) {
-            if (gI1) rc = polyphase(false, g1p, gI1, B, C, H, W, st);
-            if (rc == OFR_OK && gI2) rc = polyphase(false, g2p, gI2, B, C, H, W, st);
-            return rc;
-        }
+        int rc = ofr::corr_bwd_umma(f1, f2, gO, gI1, gI2, cg, st, true, true);
         if (rc != OFR_ENOTSUP) return rc;
         rc = OFR_OK;
         if (gI2) rc = polyphase(true, f1, f1p, B, C, H, W, st);

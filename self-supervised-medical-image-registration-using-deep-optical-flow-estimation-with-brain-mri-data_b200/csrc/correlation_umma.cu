@@ -528,7 +528,8 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
     if (warp < 4) {
         const int yp = 2 * warp + (lane >> 4), xp = lane & 15;
         const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
-        float* o = gI + (size_t)b * C * hw + (y0 + yp) * W + x0 + xp;
+        const SrcView dv = src_view(SrcMap{sm.dst_full, 0}, b, C, H, W);
+        float* o = gI + dv.base + (y0 + yp) * dv.rs + (x0 + xp) * dv.xs;
         for (int c0 = 0; c0 < C; c0 += 16) {
             uint32_t v[16];
             asm volatile(
@@ -540,7 +541,7 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) __stcs(o + (size_t)(c0 + j) * hw, __uint_as_float(v[j]) * g.scale);
+            for (int j = 0; j < 16; ++j) __stcs(o + (size_t)(c0 + j) * dv.cs, __uint_as_float(v[j]) * g.scale);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -593,7 +594,7 @@ int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& 
 }
 
 int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
-                  cudaStream_t st, bool full_src) {
+                  cudaStream_t st, bool full_src, bool full_dst) {
     if (!umma_enabled()) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % 16) || g.C < 16 || g.C > 256) return OFR_ENOTSUP;
@@ -605,7 +606,7 @@ int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1,
     if (nblk >= (1ll << 31)) return OFR_ENOTSUP;
     OFR_CUDA(cudaFuncSetAttribute(corr_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSMEM));
     corr_bwd_umma_kernel<<<(unsigned)nblk, BTHREADS, BSMEM, st>>>(f1, f2, gO, gI1, gI2, g, tiles_x, tiles_y, ndir,
-                                                                  gI1 ? 0 : 1, SrcMap{full_src ? 1 : 0, 0});
+                                                                  gI1 ? 0 : 1, SrcMap{full_src ? 1 : 0, full_dst ? 1 : 0});
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
