@@ -69,7 +69,9 @@ int ofr_corr_out_shape(int H, int W, int pad, int k, int md, int s1, int s2,
                        int* D, int* Hout, int* Wout);
 /* Bytes of scratch the fast path of this geometry wants (0 = none).  backward != 0 sizes the backward call.
  * The stride2 = 2 configuration (FlowNetC) runs as four stride-1 correlations on the 2x2 polyphase components of
- * the inputs and needs room for the split copies.  Passing ws = NULL (or too little) is legal: the call then takes a
+ * the inputs.  Shapes that tile (class images multiples of 8 x 16, C a multiple of 16, C <= 256 for the backward) run
+ * on the tcgen05 tensor cores, address every tensor in place and need no scratch (0 is returned); the FP32 FMA
+ * fallback needs room for the split copies.  Passing ws = NULL (or too little) is legal: the call then takes a
  * slower kernel that needs no scratch. */
 size_t ofr_corr_workspace(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2, int backward);
 int ofr_corr_fwd(const float* f1, const float* f2, float* out,

@@ -28,6 +28,7 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
 // correlation_umma.cu.  OFR_ENOTSUP when the geometry does not tile.
 // `g` is the class geometry (B*4 class images of H/2 x W/2).  full_src: the inputs (f1, f2, gO) are the operator's own
 // [B][C][H][W] tensors and are read in place with stride 2; the outputs are always written in the class layout.
+bool corr_umma_applicable(const CorrGeom& class_geom, bool backward);
 int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src = false,
                   bool full_dst = false);  // full_dst: `out` is the operator's own [B][D*D][H][W] tensor (no merge pass)
 int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,

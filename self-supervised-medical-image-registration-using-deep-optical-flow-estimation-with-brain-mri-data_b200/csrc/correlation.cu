@@ -397,6 +397,7 @@ extern "C" int ofr_corr_out_shape(int H, int W, int pad, int k, int md, int s1, 
 extern "C" size_t ofr_corr_workspace(int B, int C, int H, int W, int pad, int k, int md, int s1, int s2, int backward) {
     CorrGeom g;
     if (!make_geom(g, B, C, H, W, pad, k, md, s1, s2) || !polyphase_ok(g)) return 0;
+    if (ofr::corr_umma_applicable(class_geom(g), backward != 0)) return 0;  // tensor-core path: everything in place
     return poly_ws_bytes(g, backward != 0);
 }
 
@@ -413,6 +414,10 @@ extern "C" int ofr_corr_fwd_act(const float* f1, const float* f2, float* out, in
     if (!(negative_slope >= 0.f)) return OFR_EINVAL;
     g.slope = negative_slope;
     cudaStream_t st = (cudaStream_t)stream;
+    if (polyphase_ok(g)) {  // tensor-core kernel: reads f1 / f2 and writes the cost volume in place (stride 2), no scratch
+        const int rc = ofr::corr_fwd_umma(f1, f2, out, class_geom(g), st, true, true);
+        if (rc != OFR_ENOTSUP) return rc;
+    }
     if (polyphase_ok(g) && ws && !(reinterpret_cast<uintptr_t>(ws) & 255u) && ws_bytes >= poly_ws_bytes(g, false) &&
         ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(out)) {
         // FlowNetC: Correlation(20,1,20,1,2) (FlowNetC.py:31) = 4 x stride-1 correlation (R = 10) on the class images
@@ -421,10 +426,7 @@ extern "C" int ofr_corr_fwd_act(const float* f1, const float* f2, float* out, in
         float* f2p = (float*)((char*)ws + feat);
         float* outp = (float*)((char*)ws + 2 * feat);
         const CorrGeom cg = class_geom(g);
-        // tensor-core kernel: reads f1 / f2 in place (stride 2), no split pass
-        int rc = ofr::corr_fwd_umma(f1, f2, out, cg, st, true, true);
-        if (rc != OFR_ENOTSUP) return rc;
-        rc = polyphase(true, f1, f1p, B, C, H, W, st);
+        int rc = polyphase(true, f1, f1p, B, C, H, W, st);
         if (rc == OFR_OK) rc = polyphase(true, f2, f2p, B, C, H, W, st);
         if (rc != OFR_OK) return rc;
         rc = ofr::corr_fwd_tma(f1p, f2p, outp, cg, st);
@@ -459,6 +461,10 @@ extern "C" int ofr_corr_bwd(const float* f1, const float* f2, const float* gO, f
     if (!f1 || !f2 || !gO || !make_geom(g, B, C, H, W, pad, k, md, s1, s2)) return OFR_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (!gI1 && !gI2) return OFR_OK;
+    if (polyphase_ok(g)) {  // tensor-core kernel: f1 / f2 / gO read and both gradients written in place, no scratch
+        const int rc = ofr::corr_bwd_umma(f1, f2, gO, gI1, gI2, class_geom(g), st, true, true);
+        if (rc != OFR_ENOTSUP) return rc;
+    }
     if (polyphase_ok(g) && ws && !(reinterpret_cast<uintptr_t>(ws) & 255u) && ws_bytes >= poly_ws_bytes(g, true) &&
         ofr::aligned16(f1) && ofr::aligned16(f2) && ofr::aligned16(gO) && (!gI1 || ofr::aligned16(gI1)) &&
         (!gI2 || ofr::aligned16(gI2))) {
@@ -471,10 +477,7 @@ extern "C" int ofr_corr_bwd(const float* f1, const float* f2, const float* gO, f
         float* g1p = (float*)(w + 2 * feat + vol);
         float* g2p = (float*)(w + 3 * feat + vol);
         const CorrGeom cg = class_geom(g);
-        // tensor-core kernel: reads f1 / f2 / gO in place (stride 2), no split passes
-        int rc = ofr::corr_bwd_umma(f1, f2, gO, gI1, gI2, cg, st, true, true);
-        if (rc != OFR_ENOTSUP) return rc;
-        rc = OFR_OK;
+        int rc = OFR_OK;
         if (gI2) rc = polyphase(true, f1, f1p, B, C, H, W, st);
         if (rc == OFR_OK && gI1) rc = polyphase(true, f2, f2p, B, C, H, W, st);
         if (rc == OFR_OK) rc = polyphase(true, gO, gOp, B, g.D * g.D, H, W, st);

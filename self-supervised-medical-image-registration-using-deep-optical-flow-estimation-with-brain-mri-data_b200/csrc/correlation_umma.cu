@@ -577,9 +577,20 @@ static bool umma_enabled() {
 // Class-image correlation (k = 1, s1 = s2 = 1, pad = md = 10) on the tensor cores.  OFR_ENOTSUP (nothing launched) when
 // the geometry does not tile (the caller then uses the FMA kernels).  OFR_CORR_UMMA=0 in the environment disables it
 // (A/B measurements only).
+// host-side predicate: will corr_fwd_umma / corr_bwd_umma take this class geometry?  (ofr_corr_workspace uses it: the
+// tensor-core kernels address the operator's tensors in place and need no scratch)
+bool corr_umma_applicable(const CorrGeom& g, bool backward) {
+    if (!umma_enabled()) return false;
+    if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return false;
+    if ((g.W % UTW) || (g.H % UTH) || (g.C % 16) || g.C < 16) return false;
+    if (backward && g.C > 256) return false;
+    if ((long long)g.C * g.H * g.W * 4 >= (1ll << 30) || (long long)UD * UD * g.H * g.W * 4 >= (1ll << 30)) return false;
+    return true;
+}
+
 int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& g, cudaStream_t st, bool full_src,
                   bool full_dst) {
-    if (!umma_enabled()) return OFR_ENOTSUP;
+    if (!corr_umma_applicable(g, false)) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % UKT) || g.C < UKT) return OFR_ENOTSUP;
     if ((long long)g.C * g.H * g.W >= (1ll << 30)) return OFR_ENOTSUP;
@@ -595,7 +606,7 @@ int corr_fwd_umma(const float* f1, const float* f2, float* out, const CorrGeom& 
 
 int corr_bwd_umma(const float* f1, const float* f2, const float* gO, float* gI1, float* gI2, const CorrGeom& g,
                   cudaStream_t st, bool full_src, bool full_dst) {
-    if (!umma_enabled()) return OFR_ENOTSUP;
+    if (!corr_umma_applicable(g, true)) return OFR_ENOTSUP;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return OFR_ENOTSUP;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % 16) || g.C < 16 || g.C > 256) return OFR_ENOTSUP;
     if ((long long)g.C * g.H * g.W * 4 >= (1ll << 30) || (long long)UD * UD * g.H * g.W * 4 >= (1ll << 30)) return OFR_ENOTSUP;
