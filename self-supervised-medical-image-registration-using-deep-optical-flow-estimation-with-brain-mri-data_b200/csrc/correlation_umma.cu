@@ -406,8 +406,10 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
         const int nk = h ? BK1 / 4 : BK0 / 4, cbase = h ? BK0 : 0;
 #pragma unroll
         for (int i = 0; i < BB_TASKS; ++i) {
+            // 8 consecutive tasks = 8 consecutive channels of one chunk: a quarter-warp's 16-byte stores then fill one
+            // 128-byte core-matrix row group (chunk-fastest order put two tasks of a quarter-warp on the same banks)
             const int t = tid + BTHREADS * i;
-            const int c = t / nk, kq = t - c * nk;
+            const int grp = t >> 3, cblk = grp / nk, kq = grp - cblk * nk, c = cblk * 8 + (t & 7);
             const int xx0 = x0 - UR + cbase + kq * 4;
             unsigned m = 0;
 #pragma unroll
@@ -415,7 +417,7 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
                 if (c < C && cbase + kq * 4 + e < UNW && (unsigned)(xx0 + e) < (unsigned)W) m |= 1u << e;
             b_msk[h][i] = m;
             b_off[h][i] = c * fv.cs + xx0 * fv.xs;
-            b_dst[h][i] = kq * ((C + 1) * 4) + c * 4;
+            b_dst[h][i] = c < C ? kq * ((C + 1) * 4) + c * 4 : -1;
         }
     }
 
@@ -495,7 +497,7 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
             // B: the prefetched features of this stage
 #pragma unroll
             for (int i = 0; i < BB_TASKS; ++i) {
-                if (b_msk[h][i] || (tid + BTHREADS * i) / nk < C) {
+                if (b_dst[h][i] >= 0) {
                     float4 hv, lv;
                     split_tf32(pb[h][i][0], hv.x, lv.x);
                     split_tf32(pb[h][i][1], hv.y, lv.y);
