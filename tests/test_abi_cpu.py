@@ -51,6 +51,13 @@ def test_host_side_argument_checks_need_no_gpu(built):
     assert lib.ofr_corr_fwd(1, 1, 1, 1, 1, 8, 8, 4, 2, 4, 1, 1, None, 0, None) == 1  # even kernel size
     assert lib.ofr_corr_workspace(24, 32, 128, 128, 4, 1, 4, 1, 1, 0) == 0        # PWC path needs no scratch
     assert lib.ofr_corr_workspace(1, 4, 32, 32, 20, 1, 20, 1, 2, 0) >= 4 * (2 * 4 + 441) * 32 * 32
+    # FlowNetC shapes that tile (class images multiples of 8 x 16, C % 16 == 0) run on the tensor-core kernels, which
+    # address every tensor in place: no scratch either; C > 256 only in the forward
+    assert lib.ofr_corr_workspace(24, 256, 64, 64, 20, 1, 20, 1, 2, 0) == 0
+    assert lib.ofr_corr_workspace(24, 256, 64, 64, 20, 1, 20, 1, 2, 1) == 0
+    assert lib.ofr_corr_workspace(1, 512, 32, 32, 20, 1, 20, 1, 2, 0) == 0
+    assert lib.ofr_corr_workspace(1, 512, 32, 32, 20, 1, 20, 1, 2, 1) > 0
+    assert lib.ofr_corr_workspace(1, 256, 24, 24, 20, 1, 20, 1, 2, 0) > 0           # 12 x 12 class images do not tile
     assert lib.ofr_resample_fwd(None, None, None, 1, 1, 4, 4, 4, 4, 0, None) == 1
     assert lib.ofr_loss_workspace(0) == 0 and lib.ofr_loss_workspace(9) == 0
     assert lib.ofr_loss_workspace(7) > 0
