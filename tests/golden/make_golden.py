@@ -176,8 +176,41 @@ def main():
         out[f"{tag}_out"] = F.grid_sample(img32, grid, mode="bilinear", padding_mode="border",
                                           align_corners=True).numpy()
     np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
+    make_regloss(ref_models, ref_loss)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
+def make_regloss(ref_models, ref_loss):
+    """regloss.npz: the reference's own chain ``warped = [stn(flow, moving) for flow in flows]`` (models.py:277) ->
+    ``OFEloss(flows, warped, fixed)`` (train.py:56), values and d total / d flow by autograd through the reference code.
+    Own generator, so the other fixtures do not depend on it."""
+    g = torch.Generator().manual_seed(66)
+    stn = ref_models.opticalFlowReg.stn
+    B = 2
+    fixed = torch.rand(B, 1, 32, 32, generator=g)
+    moving = torch.rand(B, 1, 32, 32, generator=g)
+    scales = [(32, 32), (16, 16), (8, 8), (4, 4)]
+    flows = [(torch.randn(B, 2, h, w, generator=g) * 1.5).requires_grad_(True) for h, w in scales]
+    warped = [stn(None, fl, moving) for fl in flows]
+    p, c, s, tot = ref_loss.OFEloss(flows, warped, fixed)
+    tot.backward()
+    out = {"fixed": fixed.numpy(), "moving": moving.numpy(),
+           "ofe": np.array([p.item(), c.item(), s.item(), tot.item()], dtype=np.float64)}
+    for i, (fl, wp) in enumerate(zip(flows, warped)):
+        out[f"flow{i}"] = fl.detach().numpy()
+        out[f"warped{i}"] = wp.detach().numpy()
+        out[f"gflow{i}"] = fl.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "regloss.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-regloss" in sys.argv:  # add the newest fixture without rewriting the others
+        sys.path.insert(0, REF)
+        sys.path.insert(0, os.path.join(REF, "PWC", "models"))
+        _install_stubs()
+        _loss = importlib.import_module("loss")
+        _loss.device = torch.device("cpu")
+        make_regloss(importlib.import_module("models"), _loss)
+        print("wrote regloss.npz")
+    else:
+        main()

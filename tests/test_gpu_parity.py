@@ -409,6 +409,25 @@ def test_registration_loss_equals_stn_then_ofeloss(ofr):
         close(g.double().cpu() * keep, r.double() * keep, atol=1e-6, rtol=1e-4, what=f"regloss gflow[{i}]")
 
 
+def test_registration_loss_vs_reference_golden(ofr, golden):
+    """The fused kernels against the reference's own chain stn -> OFEloss run on the same inputs (regloss.npz, generated
+    by tests/golden/make_golden.py from models.py:256-268,277 and loss.py:66-84): warped images, the four terms, and
+    d total / d flow away from the pixels where the photometric derivative is ill-conditioned in float32."""
+    g = golden("regloss")
+    fixed, moving = torch.from_numpy(g["fixed"]).to(DEV), torch.from_numpy(g["moving"]).to(DEV)
+    flows = [torch.from_numpy(g[f"flow{i}"]).to(DEV).requires_grad_(True) for i in range(4)]
+    terms, warped = ofr.registration_loss(flows, moving, fixed)
+    np.testing.assert_allclose([t.item() for t in terms], g["ofe"], rtol=2e-6)
+    grads = torch.autograd.grad(terms[3], flows)
+    for i in range(4):
+        close(warped[i], torch.from_numpy(g[f"warped{i}"]), atol=1e-6, what=f"regloss golden warped{i}")
+        h, w = flows[i].shape[2:]
+        diff = torch.nn.functional.interpolate(fixed, (h, w), mode="bilinear", align_corners=False) - warped[i]
+        keep = (diff.abs() > 1e-3).double().cpu()
+        close(grads[i].double().cpu() * keep, torch.from_numpy(g[f"gflow{i}"]).double() * keep, atol=1e-6, rtol=1e-4,
+              what=f"regloss golden gflow{i}")
+
+
 def test_registration_loss_argument_errors(ofr):
     fixed = torch.rand(2, 1, 16, 16).to(DEV)
     flow = torch.zeros(2, 2, 16, 16).to(DEV)

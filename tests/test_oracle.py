@@ -168,6 +168,21 @@ def test_loss_gradients_vs_reference_golden(golden):
         np.testing.assert_allclose(warped[i].grad.numpy(), g[f"gwarped{i}"], rtol=1e-5, atol=1e-6)
 
 
+def test_registration_chain_vs_reference_golden(golden):
+    """The reference's own chain stn -> OFEloss (models.py:277, train.py:56), values and d total / d flow through both
+    (regloss.npz): the oracle restatement in float32, the reference's arithmetic."""
+    g = golden("regloss")
+    fixed, moving = T(g["fixed"], torch.float32), T(g["moving"], torch.float32)
+    flows = [T(g[f"flow{i}"], torch.float32).requires_grad_(True) for i in range(4)]
+    warped = [oracle.stn_warp(f, moving) for f in flows]
+    res = oracle.ofe_loss(flows, warped, fixed)
+    np.testing.assert_allclose([float(t.detach()) for t in res], g["ofe"], rtol=2e-6)
+    res[3].backward()
+    for i in range(4):
+        np.testing.assert_allclose(warped[i].detach().numpy(), g[f"warped{i}"], atol=1e-6)
+        np.testing.assert_allclose(flows[i].grad.numpy(), g[f"gflow{i}"], rtol=1e-4, atol=1e-5)
+
+
 def test_loss_degenerate_cases(golden):
     g = golden("loss")
     fixed = T(g["fixed"], torch.float32)
