@@ -104,6 +104,11 @@ int ofr_corr_bwd(const float* f1, const float* f2, const float* gO,
  *                      g=2(p+flow)/max(W-1,1)-1, grid_sample(zeros, align_corners=False),
  *                      result zeroed where the warped ones-mask < 0.9999.
  * in1 [B,C,Hin,Win], flow [B,2,Hf,Wf], out [B,C,Hf,Wf].  STN and PWC need Hin==Hf, Win==Wf.
+ * Images must be finite: with C <= 2 the zeros-padding modes (STN, PWC) load border-clamped taps and give the taps
+ * grid_sample would skip a weight of exactly 0, so an Inf/NaN border pixel would leak into samples that fall outside
+ * (0 * Inf); the C > 2 kernels predicate the loads instead.  Flows may be anything (huge / NaN positions are clamped).
+ * kernel_size > 1 of upstream's Resample2d is not provided (no reference call site uses it; upstream's own kernel
+ * reads out of bounds for it): the Python module raises NotImplementedError.
  */
 enum {
     OFR_WARP_FLOWNET2 = 0,
@@ -171,6 +176,14 @@ int ofr_chnorm_diff_bwd(const float* x, const float* x2, const float* out, const
  * `fixed` is the full-resolution fixed image [B,1,Hs,Ws]; its bilinear
  * (align_corners=False) resize to each scale is done inside the kernel.
  * All reductions accumulate in float64 in a fixed order (bitwise reproducible).
+ * Any batch / image size is accepted (beyond 8192 (image, row-strip) items per scale a CTA walks several items).
+ * Scales whose width is not a multiple of 4, or whose tensors are not 16-byte aligned (a contiguous view with an odd
+ * storage offset), take scalar instead of 128-bit accesses -- same results.
+ * NCC of a constant image (documented divergence, pinned by tests/golden/ncc_const.npz): loss.py:58-60 returns
+ * corr = 1 (loss 0) only if `x - mean(x)` is identically zero in float32, i.e. for constants whose float32 mean is
+ * exact (0, 0.5, ...); for other constants (0.7, 0.3 on some reduction orders) float32 rounding noise of torch.mean
+ * decides and the reference returns a loss of ~1.  This library returns corr = 1 (loss 0, zero gradient) for every
+ * image with min == max, and whenever a centred second moment is not positive in float64.
  */
 #define OFR_LOSS_MAX_SCALES 8
 #define OFR_LOSS_STATE_DOUBLES 16 /* per scale, see loss.cu for the slot layout */

@@ -180,3 +180,49 @@ def channelnorm(x):
 def channelnorm_backward(x, out, grad_out):
     """Upstream backward: gO * x / (out + 1e-8)   [UPSTREAM-RECALLED, SURVEY.md 2.1]."""
     return grad_out * x / (out + 1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nn.Module forms with the flownet2 constructor signatures, so the tests can put the oracle behind the reference's own
+# model classes (tests/test_gpu_reference_models.py) exactly where the CUDA layers go.
+class _ChannelNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        out = channelnorm(x)
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        return channelnorm_backward(x, out, grad_out)
+
+
+class Correlation(torch.nn.Module):
+    def __init__(self, pad_size=0, kernel_size=0, max_displacement=0, stride1=1, stride2=2, corr_multiply=1):
+        super().__init__()
+        self.geom = (pad_size, kernel_size, max_displacement, stride1, stride2)
+
+    def forward(self, input1, input2):
+        return correlation(input1, input2, *self.geom)
+
+
+class Resample2d(torch.nn.Module):
+    def __init__(self, kernel_size=1, bilinear=True):
+        super().__init__()
+        assert kernel_size == 1
+        self.bilinear = bilinear
+
+    def forward(self, input1, input2):
+        return resample2d(input1, input2, self.bilinear)
+
+
+class ChannelNorm(torch.nn.Module):
+    def __init__(self, norm_deg=2):
+        super().__init__()
+
+    def forward(self, input1):
+        return _ChannelNormFn.apply(input1)
+
+
+MODULES = {"Correlation": Correlation, "Resample2d": Resample2d, "ChannelNorm": ChannelNorm}

@@ -12,10 +12,13 @@ from ._lib import build, launch_count, LIB_PATH, EXPORTS
 from .layers import (Correlation, Resample2d, ChannelNorm, stn_warp, stn_warp_multi, pwc_warp, channelnorm_diff, spatial_correlation_sample,
                      correlation_out_shape)
 from .loss import OFEloss, registration_loss, photometric_loss, correlation_loss, smoothness_loss
+from .registration import OpticalFlowReg, grid_generator, round_clamp_labels
+from .pairs import ElasticPairGenerator, control_grid_size
 from .shims import install as install_shims, uninstall as uninstall_shims
 
 __all__ = [
     "Correlation", "Resample2d", "ChannelNorm", "stn_warp", "stn_warp_multi", "pwc_warp", "channelnorm_diff", "spatial_correlation_sample",
     "correlation_out_shape", "OFEloss", "registration_loss", "photometric_loss", "correlation_loss", "smoothness_loss",
+    "OpticalFlowReg", "grid_generator", "round_clamp_labels", "ElasticPairGenerator", "control_grid_size",
     "install_shims", "uninstall_shims", "build", "launch_count", "LIB_PATH", "EXPORTS",
 ]

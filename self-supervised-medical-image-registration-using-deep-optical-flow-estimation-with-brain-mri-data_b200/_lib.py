@@ -64,18 +64,38 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile every kernel for sm_100a into one shared library, in-tree."""
+def build(force=False, verbose=False, jobs=None):
+    """Compile every kernel for sm_100a into one shared library, in-tree (one nvcc per source file, in parallel, then
+    one link)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        return src, obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=jobs or min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, cmd, res in results:
+        if verbose or res.returncode != 0:
+            print(" ".join(cmd))
+            print(res.stdout)
+            print(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed compiling {src}:\n" + res.stderr[-4000:])
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + \
+          [obj for _, obj, _, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        print(" ".join(cmd))
-        print(res.stdout)
-        print(res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libofr_b200.so:\n" + res.stderr[-4000:])
+        raise RuntimeError("nvcc failed linking libofr_b200.so:\n" + res.stderr[-4000:])
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

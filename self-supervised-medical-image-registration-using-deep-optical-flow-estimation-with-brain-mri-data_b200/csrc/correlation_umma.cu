@@ -25,8 +25,6 @@
 // measured at 1096 TFLOP/s (tf32, N = 256) against 72 TFLOP/s of FP32 FMA.
 #include "corr_internal.cuh"
 
-#include <cstdlib>
-
 namespace {
 
 constexpr int UM = 128;          // pixels per tile = MMA M
@@ -138,7 +136,7 @@ __global__ void __launch_bounds__(UTHREADS, 2) corr_fwd_umma_kernel(const float*
     const int tyi = bid % tiles_y;
     const int b = bid / tiles_y;
     const int x0 = txi * UTW, y0 = tyi * UTH;
-    const int H = g.H, W = g.W, hw = H * W, C = g.C;
+    const int H = g.H, W = g.W, C = g.C;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[0])));
@@ -355,7 +353,7 @@ __device__ __forceinline__ void corr_bwd_umma_body(const float* __restrict__ fea
     const int tyi = bid % tiles_y;
     const int b = bid / tiles_y;
     const int x0 = txi * UTW, y0 = tyi * UTH;
-    const int H = g.H, W = g.W, hw = H * W, C = g.C;
+    const int H = g.H, W = g.W, C = g.C;
     const uint32_t ncols = C <= 32 ? 32u : C <= 64 ? 64u : C <= 128 ? 128u : 256u;
 
     if (tid == 0) {
@@ -568,21 +566,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) corr_bwd_umma_kernel(const float*
 
 namespace ofr {
 
-static bool umma_enabled() {
-    static const bool enabled = [] {
-        const char* e = getenv("OFR_CORR_UMMA");
-        return !(e && e[0] == '0');
-    }();
-    return enabled;
-}
-
 // Class-image correlation (k = 1, s1 = s2 = 1, pad = md = 10) on the tensor cores.  OFR_ENOTSUP (nothing launched) when
-// the geometry does not tile (the caller then uses the FMA kernels).  OFR_CORR_UMMA=0 in the environment disables it
-// (A/B measurements only).
+// the geometry does not tile (the caller then uses the FMA kernels).  No process-global switch: the choice is a pure
+// function of the geometry.
 // host-side predicate: will corr_fwd_umma / corr_bwd_umma take this class geometry?  (ofr_corr_workspace uses it: the
 // tensor-core kernels address the operator's tensors in place and need no scratch)
 bool corr_umma_applicable(const CorrGeom& g, bool backward) {
-    if (!umma_enabled()) return false;
     if (!(g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == UR && g.pad == UR)) return false;
     if ((g.W % UTW) || (g.H % UTH) || (g.C % 16) || g.C < 16) return false;
     if (backward && g.C > 256) return false;

@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kHardMaxCtasPerScale = 8192;  // batches beyond this many images per scale are refused
+constexpr int kMaxCtasPerScale = 8192;  // CTAs per scale (bounds the partials workspace); beyond it a CTA loops over items
 constexpr int kNumPart = 11;           // partial slots per CTA, see enum
 
 enum { P_PHOTO = 0, P_SW, P_SF, P_SWW, P_SFF, P_SWF, P_SMOOTH, P_MINW, P_MAXW, P_MINF, P_MAXF };
@@ -44,6 +44,8 @@ struct ScaleDev {
     int rows_per_cta;  // work item = (image, strip of rows_per_cta rows)
     int strips;        // strips per image
     int tx_shift;      // the CTA's 256 threads are (1 << tx_shift) pixel-group columns x (256 >> tx_shift) row lanes
+    int vec4;          // 128-bit accesses: w % 4 == 0 and every tensor of the scale 16-byte aligned (else scalar)
+    int items;         // strips * B work items; the scale's CTAs stride over them
     // fused registration loss (ofr_regloss_*): warped = stn(flow, moving) is formed inside the kernels
     const float* moving;     // [B,1,h,w] moving image resized to this scale, or nullptr (plain OFEloss)
     float* warped_out;       // forward: the warped image is also written here (the backward reads it back)
@@ -132,11 +134,10 @@ __device__ __forceinline__ float warp_maxf(float v) {
 struct Strip {
     int s, b, y0, y1;
 };
-__device__ __forceinline__ Strip strip_of_cta(const LossParams& p) {
+__device__ __forceinline__ Strip strip_of_item(const LossParams& p, int s, int item) {
     Strip st;
-    st.s = scale_of_cta(p, blockIdx.x);
-    const ScaleDev& sc = p.sc[st.s];
-    const int item = blockIdx.x - p.cta_begin[st.s];
+    st.s = s;
+    const ScaleDev& sc = p.sc[s];
     st.b = item / sc.strips;
     st.y0 = (item - st.b * sc.strips) * sc.rows_per_cta;
     st.y1 = min(st.y0 + sc.rows_per_cta, sc.h);
@@ -280,15 +281,19 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 4) loss_partial_kernel(const __grid_constant__ LossParams p,
                                                                             double* __restrict__ partials) {
     __shared__ double red[kNumPart][kThreads / 32];
-    const Strip st = strip_of_cta(p);
+    const int s = scale_of_cta(p, blockIdx.x);
+    const int c0 = blockIdx.x - p.cta_begin[s], nc = p.cta_begin[s + 1] - p.cta_begin[s];
     double acc[7];
     float mm[4] = {3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f};
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k] = 0.0;
-    if (p.sc[st.s].w % 4 == 0)
-        partial_body<4, FUSED>(p, st, mm, acc);
-    else
-        partial_body<1, FUSED>(p, st, mm, acc);
+    for (int item = c0; item < p.sc[s].items; item += nc) {  // one item per CTA unless strips * B > kMaxCtasPerScale
+        const Strip st = strip_of_item(p, s, item);
+        if (p.sc[s].vec4)
+            partial_body<4, FUSED>(p, st, mm, acc);
+        else
+            partial_body<1, FUSED>(p, st, mm, acc);
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const double v = warp_sum(acc[k]);
@@ -580,10 +585,10 @@ __device__ __forceinline__ void bwd_body_fused(const LossParams& p, const Strip&
 struct BwdCoef {
     float cp, cs, k1, k2, mf, mw;
 };
-__device__ __forceinline__ BwdCoef bwd_coef(const LossParams& p, const Strip& st, const double* __restrict__ grad4,
+__device__ __forceinline__ BwdCoef bwd_coef(const LossParams& p, int s, const double* __restrict__ grad4,
                                             const double* __restrict__ state) {
-    const double* sd = state + st.s * OFR_LOSS_STATE_DOUBLES;
-    const double wi = 0.05 * (double)(st.s + 1), inv_n = 1.0 / (double)p.n, Bd = (double)p.B;
+    const double* sd = state + s * OFR_LOSS_STATE_DOUBLES;
+    const double wi = 0.05 * (double)(s + 1), inv_n = 1.0 / (double)p.n, Bd = (double)p.B;
     const double gP = grad4[0] + grad4[3], gC = grad4[1] + grad4[3], gS = grad4[2] + grad4[3];
     BwdCoef c;
     c.cp = (float)(gP * inv_n * p.gamma * wi / Bd);            // d total / d photometric-sum
@@ -602,23 +607,31 @@ __device__ __forceinline__ BwdCoef bwd_coef(const LossParams& p, const Strip& st
 __global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const __grid_constant__ LossParams p,
                                                             const double* __restrict__ grad4,
                                                             const double* __restrict__ state) {
-    const Strip st = strip_of_cta(p);
-    const BwdCoef c = bwd_coef(p, st, grad4, state);
-    if (p.sc[st.s].w % 4 == 0)
-        bwd_body<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
-    else
-        bwd_body<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    const int s = scale_of_cta(p, blockIdx.x);
+    const int c0 = blockIdx.x - p.cta_begin[s], nc = p.cta_begin[s + 1] - p.cta_begin[s];
+    const BwdCoef c = bwd_coef(p, s, grad4, state);
+    for (int item = c0; item < p.sc[s].items; item += nc) {
+        const Strip st = strip_of_item(p, s, item);
+        if (p.sc[s].vec4)
+            bwd_body<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+        else
+            bwd_body<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 2) regloss_bwd_kernel(const __grid_constant__ LossParams p,
                                                                   const double* __restrict__ grad4,
                                                                   const double* __restrict__ state) {
-    const Strip st = strip_of_cta(p);
-    const BwdCoef c = bwd_coef(p, st, grad4, state);
-    if (p.sc[st.s].w % 4 == 0)
-        bwd_body_fused<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
-    else
-        bwd_body_fused<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    const int s = scale_of_cta(p, blockIdx.x);
+    const int c0 = blockIdx.x - p.cta_begin[s], nc = p.cta_begin[s + 1] - p.cta_begin[s];
+    const BwdCoef c = bwd_coef(p, s, grad4, state);
+    for (int item = c0; item < p.sc[s].items; item += nc) {
+        const Strip st = strip_of_item(p, s, item);
+        if (p.sc[s].vec4)
+            bwd_body_fused<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+        else
+            bwd_body_fused<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    }
 }
 
 int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const ofr_loss_scale_t* scales, int n,
@@ -636,17 +649,22 @@ int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const 
             if ((long long)s.h * s.w >= (1ll << 30)) return OFR_EINVAL;
             // thread shape: tx_n = power of two covering the pixel groups of a row (at most 256), the other
             // 256 / tx_n thread lanes each walk kRPT consecutive rows -> rows per CTA
-            const int gw = (s.w % 4 == 0) ? s.w / 4 : s.w;
+            // 128-bit path only when every tensor of the scale can take it (a contiguous view with an odd storage
+            // offset is legal input: it runs on the scalar path instead of faulting)
+            const bool vec4 = s.w % 4 == 0 && ofr::aligned16(s.warped) && ofr::aligned16(s.flow) &&
+                              ofr::aligned16(s.g_warped) && ofr::aligned16(s.g_flow);
+            const int gw = vec4 ? s.w / 4 : s.w;
             int tx_shift = 0;
             while ((1 << tx_shift) < gw && tx_shift < 8) ++tx_shift;
             int rows = (kThreads >> tx_shift) * kRPT;
             if (rows > s.h) rows = (s.h + kRPT - 1) / kRPT * kRPT;
             int strips = (s.h + rows - 1) / rows;
-            if ((long long)strips * B > kHardMaxCtasPerScale) return OFR_ENOTSUP;  // absurd batch size
-            p.sc[i] = ScaleDev{s.warped, s.flow, s.g_warped, s.g_flow, s.h, s.w, rows, strips, tx_shift};
-            at += strips * B;
+            const long long items = (long long)strips * B;
+            if (items >= (1ll << 31)) return OFR_EINVAL;
+            p.sc[i] = ScaleDev{s.warped, s.flow, s.g_warped, s.g_flow, s.h, s.w, rows, strips, tx_shift, vec4 ? 1 : 0, (int)items};
+            at += (int)(items < kMaxCtasPerScale ? items : kMaxCtasPerScale);
         } else {
-            p.sc[i] = ScaleDev{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, 0};
+            p.sc[i] = ScaleDev{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, 0, 0, 0};
         }
     }
     p.cta_begin[OFR_LOSS_MAX_SCALES] = at;
@@ -660,9 +678,9 @@ size_t ws_bytes_for(int total_ctas) { return ofr::align_up(sizeof(double) * kNum
 
 extern "C" size_t ofr_loss_workspace(int n_scales) {
     if (n_scales < 1 || n_scales > OFR_LOSS_MAX_SCALES) return 0;
-    // upper bound that does not depend on the batch: fill_params never uses more than kHardMaxCtasPerScale CTAs
-    // per scale.
-    return ws_bytes_for(kHardMaxCtasPerScale * n_scales);
+    // upper bound that does not depend on the batch: fill_params never uses more than kMaxCtasPerScale CTAs per scale
+    // (larger batches / images make every CTA walk several (image, strip) items).
+    return ws_bytes_for(kMaxCtasPerScale * n_scales);
 }
 
 extern "C" int ofr_loss_fwd(const float* fixed, int B, int Hs, int Ws, const ofr_loss_scale_t* scales, int n_scales,

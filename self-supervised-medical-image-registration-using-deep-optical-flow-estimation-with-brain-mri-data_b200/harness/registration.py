@@ -79,9 +79,11 @@ class RegistrationStep(nn.Module):
         return self._loss(flows, warped, fixed)
 
 
-def make_optimizer(model, lr=1e-4, eps=1e-4):
-    """Adam exactly as train.py:129 builds it (eps = lrMin default 1e-4)."""
-    return torch.optim.Adam(model.parameters(), lr=lr, eps=eps)
+def make_optimizer(model, lr=1e-4, eps=1e-4, capturable=False):
+    """Adam exactly as train.py:129 builds it (eps = lrMin default 1e-4).  ``capturable``: the step counter lives on
+    the device so that the optimizer can be part of a captured CUDA graph (same arithmetic)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    return torch.optim.Adam(params, lr=lr, eps=eps, capturable=capturable)
 
 
 def train_step(step, optimizer, pair):
@@ -90,3 +92,34 @@ def train_step(step, optimizer, pair):
     total.backward()
     optimizer.step()
     return total.detach()
+
+
+class GraphedStep:
+    """forward + loss + backward + Adam of one training step captured as ONE CUDA graph: possible
+    because nothing on the hot path synchronises the host or allocates behind the caller's back (the reference's step
+    cannot be captured: models.py:286 and loss.py:59 go through the host).  The batch is copied into a static device
+    buffer; ``replay()`` returns the (static) loss tensor.  The optimizer must be built with ``capturable=True``."""
+
+    def __init__(self, step, opt, example, warm_iters=3):
+        self.static_in = example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warm_iters):  # (with DDP: at least 11 eager iterations before capture)
+                train_step(step, opt, self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            total = step(self.static_in)[3]
+            total.backward()
+            opt.step()
+            self.loss = total.detach()
+        torch.cuda.synchronize()
+
+    def replay(self, batch=None):
+        if batch is not None:
+            self.static_in.copy_(batch, non_blocking=True)
+        self.graph.replay()
+        return self.loss

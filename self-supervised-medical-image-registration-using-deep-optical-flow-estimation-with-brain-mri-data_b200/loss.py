@@ -183,10 +183,11 @@ def registration_loss(flows, moving, fixed, lamb_da=0.5, gamma=100.0, zeta=100.0
 
 
 def _single_scale_terms(fixed, warped, flow):
-    """(photometric, ncc, smoothness) of one scale, each exactly as the reference's leaf function."""
+    """(photometric, ncc, smoothness) of one scale as the reference's leaf functions return them: unweighted float32
+    0-dim tensors (the kernels accumulate in float64; the cast is the only float32 rounding)."""
     # with n = 1 the weight is 0.05: choose coefficients so that the returned terms are unweighted
     p, c, s, _ = OFEloss([flow], [warped], fixed, lamb_da=20.0, gamma=20.0, zeta=20.0)
-    return p, c, s
+    return p.to(torch.float32), c.to(torch.float32), s.to(torch.float32)
 
 
 def photometric_loss(fixed, warped):

@@ -177,6 +177,7 @@ def main():
                                           align_corners=True).numpy()
     np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
     make_regloss(ref_models, ref_loss)
+    make_ncc_const(ref_loss)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -203,8 +204,32 @@ def make_regloss(ref_models, ref_loss):
     np.savez_compressed(os.path.join(HERE, "regloss.npz"), **out)
 
 
+def make_ncc_const(ref_loss):
+    """ncc_const.npz: loss.py:52-64 on constant warped images.  The reference short-circuits to corr = 1 only when the
+    float32-centred tensor is identically zero (constants with an exact float32 mean); other constants are decided by
+    the rounding noise of torch.mean.  Both behaviours are pinned here; ofr_b200 returns 0 for every constant image
+    (include/ofr_b200.h, "NCC of a constant image")."""
+    g = torch.Generator().manual_seed(67)
+    fixed = torch.rand(3, 1, 32, 32, generator=g)
+    out = {"fixed": fixed.numpy(), "values": np.array([0.0, 0.5, 0.25, 0.7, 0.3], dtype=np.float32)}
+    out["ref_loss"] = np.array([ref_loss.correlation_loss(fixed, torch.full((3, 1, 16, 16), float(v))).item()
+                                for v in out["values"]], dtype=np.float64)
+    out["centred_is_zero"] = np.array([bool(torch.equal(torch.full((3, 1, 16, 16), float(v)) -
+                                                        torch.mean(torch.full((3, 1, 16, 16), float(v))),
+                                                        torch.zeros(3, 1, 16, 16))) for v in out["values"]])
+    np.savez_compressed(os.path.join(HERE, "ncc_const.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
-    if "--only-regloss" in sys.argv:  # add the newest fixture without rewriting the others
+    if "--only-ncc-const" in sys.argv:
+        sys.path.insert(0, REF)
+        _install_stubs()
+        _loss = importlib.import_module("loss")
+        _loss.device = torch.device("cpu")
+        o = make_ncc_const(_loss)
+        print("wrote ncc_const.npz", o["values"], o["ref_loss"], o["centred_is_zero"])
+    elif "--only-regloss" in sys.argv:  # add the newest fixture without rewriting the others
         sys.path.insert(0, REF)
         sys.path.insert(0, os.path.join(REF, "PWC", "models"))
         _install_stubs()

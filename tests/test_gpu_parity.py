@@ -155,6 +155,68 @@ def test_correlation_flownetc_full_size_tensor_core_forward(ofr):
     assert o[tuple(nz[0].tolist())].item() == 6.0 / 16
 
 
+def test_correlation_flownetc_full_size_tensor_core_backward(ofr):
+    """Backward of Correlation(20,1,20,1,2) at the FlowNetC shape (B=24, C=256, 64x64) -- ``corr_bwd_umma_kernel``:
+    in-place stride-2 addressing, row skipping at the top/bottom tiles, 256 TMEM columns.  (i) Euler identity of the
+    bilinear operator, <dL/df1, f1> == <gO, out> == <dL/df2, f2>; (ii) a sample of channels of both gradients against
+    the definition accumulated over all 441 displacements in float64 on the GPU; (iii) bitwise reproducible."""
+    B, C, H, W, md, s2 = 24, 256, 64, 64, 20, 2
+    g0 = torch.Generator(device=DEV).manual_seed(91)
+    f1 = torch.randn(B, C, H, W, device=DEV, generator=g0, requires_grad=True)
+    f2 = torch.randn(B, C, H, W, device=DEV, generator=g0, requires_grad=True)
+    corr = ofr.Correlation(md, 1, md, 1, s2, 1)
+    out = corr(f1, f2)
+    go = torch.randn(out.shape, device=DEV, generator=g0)
+    g1, g2 = torch.autograd.grad(out, (f1, f2), go, retain_graph=True)
+    h1, h2 = torch.autograd.grad(out, (f1, f2), go)
+    assert torch.equal(g1, h1) and torch.equal(g2, h2)
+    lhs = (go.double() * out.detach().double()).sum().item()
+    for name, g, f in (("f1", g1, f1), ("f2", g2, f2)):
+        rhs = (g.double() * f.detach().double()).sum().item()
+        assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs)), (name, lhs, rhs)
+    r, D = md // s2, 2 * (md // s2) + 1
+    cs = [0, 7, 100, 255]
+    a = f1.detach()[:, cs].double()
+    b = torch.nn.functional.pad(f2.detach()[:, cs].double(), (md, md, md, md))
+    ref1 = torch.zeros(B, len(cs), H, W, dtype=torch.float64, device=DEV)
+    ref2 = torch.zeros(B, len(cs), H + 2 * md, W + 2 * md, dtype=torch.float64, device=DEV)
+    for tj in range(-r, r + 1):
+        for ti in range(-r, r + 1):
+            gd = go[:, (tj + r) * D + (ti + r)].double().unsqueeze(1)
+            ys, xs = md + s2 * tj, md + s2 * ti
+            ref1 += gd * b[:, :, ys:ys + H, xs:xs + W]
+            ref2[:, :, ys:ys + H, xs:xs + W] += gd * a
+    ref1 /= C
+    ref2 = ref2[:, :, md:md + H, md:md + W] / C
+    close(g1[:, cs], ref1, atol=1e-7, rtol=1e-4, what="flownetc full-size dI1")
+    close(g2[:, cs], ref2, atol=1e-7, rtol=1e-4, what="flownetc full-size dI2")
+
+
+def test_resample2d_full_size(ofr):
+    """Resample2d (mode 0: pixel-unit flow, border-clamped taps; flownet2/models.py:139-176) at 24 x 1 x 512 x 512:
+    forward and both gradients against the oracle in the layer's own float32 arithmetic, bitwise reproducible."""
+    B, S = 24, 512
+    g0 = torch.Generator(device=DEV).manual_seed(92)
+    img = torch.rand(B, 1, S, S, device=DEV, generator=g0)
+    coarse = torch.randn(B, 2, S // 16, S // 16, device=DEV, generator=g0) * 6
+    flow = torch.nn.functional.interpolate(coarse, size=(S, S), mode="bilinear", align_corners=False)
+    go = torch.randn(B, 1, S, S, device=DEV, generator=g0)
+    xi, fi = img.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    out = ofr.Resample2d()(xi, fi)
+    gx, gf = torch.autograd.grad(out, (xi, fi), go, retain_graph=True)
+    hx, hf = torch.autograd.grad(out, (xi, fi), go)
+    assert torch.equal(gx, hx) and torch.equal(gf, hf)
+    xc, fc = img.cpu().requires_grad_(True), flow.cpu().requires_grad_(True)
+    ref = oracle.resample2d(xc, fc)
+    rgx, rgf = torch.autograd.grad(ref, (xc, fc), go.cpu())
+    close(out, ref, atol=1e-5, what="full-size resample2d")
+    close(gx, rgx, atol=1e-6, rtol=1e-4, what="full-size resample2d dImg")
+    close(gf, rgf, atol=1e-5, rtol=1e-4, what="full-size resample2d dFlow")
+    lhs = (go.double() * out.detach().double()).sum().item()
+    rhs = (gx.double() * img.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
 def test_correlation_is_reproducible_and_skips_unneeded_grads(ofr):
     f1 = torch.randn(2, 32, 16, 16, generator=gen(5)).to(DEV).requires_grad_(True)
     f2 = torch.randn(2, 32, 16, 16, generator=gen(6)).to(DEV)
@@ -497,6 +559,68 @@ def test_loss_degenerate_and_reproducible(ofr, golden):
     a = ofr.OFEloss(flows, warps, fixed)
     b = ofr.OFEloss(flows, warps, fixed)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_ncc_constant_image_rule(ofr, golden):
+    """NCC of constant warped images: the reference (ncc_const.npz) returns 0 when the float32 mean of the constant is
+    exact and ~1 otherwise (0.7); the kernels return 0 -- corr = 1, zero gradient -- for EVERY constant image
+    (documented divergence on a pathological input, include/ofr_b200.h)."""
+    g = golden("ncc_const")
+    fixed = torch.from_numpy(g["fixed"]).to(DEV)
+    for v, want in zip(g["values"], g["ref_loss"]):
+        w = torch.full((3, 1, 16, 16), float(v), device=DEV, requires_grad=True)
+        got = ofr.correlation_loss(fixed, w)
+        assert got.dtype == torch.float32 and got.dim() == 0     # as loss.py's leaf functions return
+        assert got.item() == 0.0
+        if want == 0.0:
+            assert got.item() == want
+        (gw,) = torch.autograd.grad(got, w)
+        assert float(gw.abs().max()) == 0.0
+
+
+def test_loss_accepts_misaligned_views_and_huge_batches(ofr):
+    """(i) contiguous views whose storage offset is not a multiple of 16 bytes must take the scalar path, not
+    fault; (ii) more (image, strip) items than the per-scale CTA cap are walked by a loop, not refused."""
+    B, S = 2, 32
+    gcpu = gen(120)
+    fixed = torch.rand(B, 1, S, S, generator=gcpu).to(DEV)
+    moving = torch.rand(B, 1, S, S, generator=gcpu).to(DEV)
+    sizes = [(32, 32), (16, 16), (8, 8)]
+    flows = [(torch.randn(B, 2, h, w, generator=gcpu) * 1.5).to(DEV) for h, w in sizes]
+    warps = [torch.rand(B, 1, h, w, generator=gcpu).to(DEV) for h, w in sizes]
+
+    def shifted(t):  # same values in a buffer whose data pointer is 4 bytes past a 16-byte boundary
+        buf = torch.empty(t.numel() + 1, device=DEV)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.is_contiguous() and v.data_ptr() % 16 == 4
+        return v
+
+    def run(fl, wp, fx, mv):
+        fl = [f.detach().requires_grad_(True) for f in fl]
+        wp = [w.detach().requires_grad_(True) for w in wp]
+        res = ofr.OFEloss(fl, wp, fx)
+        g1 = torch.autograd.grad(res[3], fl + wp)
+        fl2 = [f.detach().requires_grad_(True) for f in fl]
+        terms, warped = ofr.registration_loss(fl2, mv, fx)
+        g2 = torch.autograd.grad(terms[3], fl2)
+        return list(res) + list(g1) + list(terms) + list(warped) + list(g2)
+
+    a = run(flows, warps, fixed, moving)
+    b = run([shifted(f) for f in flows], [shifted(w) for w in warps], shifted(fixed), shifted(moving))
+    for i, (x, y) in enumerate(zip(a, b)):
+        close(y, x, atol=1e-6, rtol=1e-6, what=f"misaligned loss item {i}")
+    # (ii) 9000 images x 1 strip > 8192 CTAs per scale
+    Bb = 9000
+    fx = torch.rand(Bb, 1, 8, 8, generator=gcpu).to(DEV)
+    fl = [torch.randn(Bb, 2, 8, 8, generator=gcpu).to(DEV).requires_grad_(True)]
+    wp = [torch.rand(Bb, 1, 8, 8, generator=gcpu).to(DEV).requires_grad_(True)]
+    res = ofr.OFEloss(fl, wp, fx)
+    gg = torch.autograd.grad(res[3], fl + wp)
+    ref = oracle.ofe_loss([f.detach().cpu().double().requires_grad_(True) for f in fl],
+                          [w.detach().cpu().double().requires_grad_(True) for w in wp], fx.cpu().double())
+    np.testing.assert_allclose([float(t) for t in res], [float(t) for t in ref], rtol=2e-6)
+    assert all(bool(torch.isfinite(g_).all()) for g_ in gg)
 
 
 # =============================================================================== model level

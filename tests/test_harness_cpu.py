@@ -122,3 +122,77 @@ def test_ddp_gloo_world2_averages_shard_gradients():
     res = [q.get(timeout=10) for _ in range(2)]
     for rank, err, scale in res:
         assert err <= 1e-5 * max(scale, 1.0), (rank, err, scale)
+
+
+# ----------------------------------------------------------------------------------------- round 2: reference in situ
+def test_staged_reference_is_byte_identical():
+    """tools/stage_reference.py: baseline/_ref holds byte-for-byte copies (SHA-256 manifest) of the reference's model
+    files; where /root/reference exists the staged files are compared with it too."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    try:
+        import stage_reference
+        if stage_reference.stage() is None:
+            pytest.skip("no reference tree and nothing staged on this box")
+        assert stage_reference.check() == []
+    finally:
+        sys.path.pop(0)
+
+
+def test_reference_flownet2_runs_unmodified_with_injected_layers():
+    """harness/reference_env.py: the reference's own ``flownet2/models.py`` FlowNet2 and ``loss.py`` / ``models.py`` import
+    and run with stand-in layers at the import paths (here the oracle's, on the CPU; on the GPU box the CUDA layers:
+    tests/test_gpu_reference_models.py), and every trace is removed from sys.modules afterwards."""
+    from ofr_b200.harness import reference_env
+    if reference_env.reference_dir() is None:
+        pytest.skip("reference files not staged")
+    before = set(sys.modules)
+    with reference_env.ReferenceEnv(oracle.MODULES) as e:
+        torch.manual_seed(6)
+        net = e.flownet2()
+        assert sum(p.numel() for p in net.parameters()) == 162493554
+        kinds = {type(m) for m in net.modules()}
+        assert set(oracle.MODULES.values()) <= kinds
+        with torch.no_grad():
+            out = net(torch.rand(1, 2, 128, 128))     # (64 px would leave BatchNorm one value per channel)
+        assert out[0].shape == (1, 2, 128, 128) and out[0] is out[1]
+        stn = e.models_module().opticalFlowReg.stn
+        fl = torch.randn(1, 2, 16, 16)
+        fr = torch.rand(1, 1, 32, 32)
+        assert torch.allclose(stn(None, fl, fr), oracle.stn_warp(fl, fr), atol=1e-6)
+        assert callable(e.loss_module().OFEloss)
+    leaked = [m for m in set(sys.modules) - before if m.split(".")[0] in
+              ("flownet2", "networks", "models", "loss", "utils", "PWCNet", "monai", "matplotlib", "correlation_package")]
+    assert leaked == []
+
+
+def test_registration_wrapper_helpers():
+    """registration.py: the cached line grid equals utils.py:15-23, label rounding equals models.py:286 (np.rint + clip)."""
+    import numpy as np
+    import ofr_b200
+    g = ofr_b200.grid_generator(256)
+    want = torch.zeros(256, 256)
+    for i in range(7, 255, 16):
+        want[i, :] = 1.0
+        want[:, i] = 1.0
+    assert torch.equal(g[0, 0], want) and ofr_b200.grid_generator(256) is g
+    x = torch.tensor([[-0.7, 0.5, 1.5, 2.5, 2.51, 3.49, 3.5, 9.0]]).view(1, 1, 1, 8)
+    got = ofr_b200.round_clamp_labels(x)
+    assert torch.equal(got, torch.from_numpy(np.clip(np.rint(x.numpy()), 0, 3)))
+
+
+def test_elastic_generator_control_grid_rule():
+    """pairs.py: MONAI's create_control_grid size rule (spacing 16 + border) and that the bicubic upsampling of the
+    control grid covers the slice after the centre crop."""
+    import ofr_b200
+    assert ofr_b200.control_grid_size(256, 16) == 20 and ofr_b200.control_grid_size(512, 16) == 36
+    for size in (64, 256, 255, 512):
+        n = ofr_b200.control_grid_size(size, 16)
+        assert n * 16 >= size + 2 * 16
+
+
+def test_bench_reference_arm_is_same_config_by_default():
+    """bench.py --impl reference runs the GPU arm's batch unless --cpu-batch says otherwise (VERDICT r1 weak #8)."""
+    import importlib
+    bench = importlib.import_module("bench")
+    src = open(bench.__file__).read()
+    assert '"--cpu-batch", type=int, default=0' in src and '"same_config": batch == args.batch' in src

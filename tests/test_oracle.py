@@ -192,3 +192,16 @@ def test_loss_degenerate_cases(golden):
     np.testing.assert_allclose(z.numpy(), g["smooth_zero"], rtol=1e-6)
     # floor value: 2 channels * 64 px * (1e-18)^0.25, /2 for the pair... per image
     np.testing.assert_allclose(float(z), 2 * 64 * (1e-18) ** 0.25, rtol=1e-5)
+
+
+def test_ncc_constant_images_vs_reference_golden(golden):
+    """loss.py:58-60 on constant warped images (ncc_const.npz, produced by the reference): loss 0 when the float32 mean
+    is exact, ~1 otherwise (0.7).  The oracle reproduces both; the CUDA kernels return 0 for every constant image
+    (documented divergence, include/ofr_b200.h) -- tests/test_gpu_parity.py::test_ncc_constant_image_rule."""
+    g = golden("ncc_const")
+    fixed = torch.from_numpy(g["fixed"])
+    for v, want, zero in zip(g["values"], g["ref_loss"], g["centred_is_zero"]):
+        got = float(oracle.ncc(fixed, torch.full((3, 1, 16, 16), float(v))))
+        assert abs(got - want) <= 1e-6, (v, got, want)
+        assert (want == 0.0) == bool(zero)
+    assert g["ref_loss"][3] > 0.99   # 0.7: float32 rounding noise decides in the reference

@@ -205,6 +205,8 @@ def main():
     if os.path.exists(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
     torch.manual_seed(6)
+    from ofr_b200.profiling import ClockSampler
+    sampler = ClockSampler(0)  # clocks / throttle reasons over the whole run, written into the JSON
     names = [c[0] for c in cases(args.batch, args.size, only=args.only, dry=True)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV) if args.single else None
     rows = []
@@ -272,8 +274,10 @@ def main():
               f"{row['tflops']:6.2f} TFLOP/s", flush=True)
         del fns, first
         torch.cuda.empty_cache()
+    clocks = sampler.stop()
+    print("clocks:", clocks, flush=True)
     if args.json:
-        json.dump(dict(peak_hbm_gbs=peak, batch=args.batch, size=args.size,
+        json.dump(dict(peak_hbm_gbs=peak, batch=args.batch, size=args.size, clocks=clocks,
                        method="single+flush" if args.single else ("rotating buffer sets > L2, CUDA-graph replay" if args.graph
                                                                    else "rotating buffer sets > L2, back-to-back launches"),
                        rows=rows), open(args.json, "w"), indent=1)
