@@ -29,12 +29,12 @@ Parity pinning status (see DESIGN.md "Oracle"):
   ``tests/golden/``.
 """
 from .layers_ref import (correlation, correlation_loops, resample2d, resample2d_loops,
-                         channelnorm, channelnorm_backward, correlation_out_shape, MODULES)
+                         channelnorm, channelnorm_backward, correlation_out_shape, MODULES, Correlation_like)
 from .warp_ref import stn_warp, pwc_warp, pixel_grid
 from .loss_ref import (charbonnier, photometric, smoothness, ncc, ofe_loss)
 
 __all__ = [
     "correlation", "correlation_loops", "correlation_out_shape", "resample2d", "resample2d_loops",
     "channelnorm", "channelnorm_backward", "stn_warp", "pwc_warp", "pixel_grid",
-    "charbonnier", "photometric", "smoothness", "ncc", "ofe_loss", "MODULES",
+    "charbonnier", "photometric", "smoothness", "ncc", "ofe_loss", "MODULES", "Correlation_like",
 ]

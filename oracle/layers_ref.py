@@ -225,4 +225,9 @@ class ChannelNorm(torch.nn.Module):
         return _ChannelNormFn.apply(input1)
 
 
+def Correlation_like(layer):
+    """The oracle Correlation with the geometry of any object carrying flownet2's attribute names."""
+    return Correlation(layer.pad_size, layer.kernel_size, layer.max_displacement, layer.stride1, layer.stride2)
+
+
 MODULES = {"Correlation": Correlation, "Resample2d": Resample2d, "ChannelNorm": ChannelNorm}

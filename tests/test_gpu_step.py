@@ -28,8 +28,10 @@ def test_optical_flow_reg_wrapper_vs_reference_forward(ofr):
         pytest.skip("baseline/_ref not staged")
     torch.manual_seed(6)
     net = PWCNetHost(md=4).to(DEV)
-    x = synthetic_pairs(2, 256, seed=21).to(DEV)
-    segs = torch.randint(0, 4, (2, 2, 256, 256), generator=torch.Generator().manual_seed(22)).float().to(DEV)
+    # batch 1: the reference's forward gives grid_sample a batch-1 grid image with the batch's flow (models.py:279-281)
+    # and therefore only runs at B = 1; the wrapper itself takes any batch (checked below)
+    x = synthetic_pairs(1, 256, seed=21).to(DEV)
+    segs = torch.randint(0, 4, (1, 2, 256, 256), generator=torch.Generator().manual_seed(22)).float().to(DEV)
     with reference_env.ReferenceEnv("ofr") as e:
         models = e.models_module()
         ref = models.opticalFlowReg.__new__(models.opticalFlowReg)
@@ -40,17 +42,23 @@ def test_optical_flow_reg_wrapper_vs_reference_forward(ofr):
     with torch.no_grad():
         f, w, s, g = ofr.OpticalFlowReg(net)(x, segs)
     assert len(f) == len(rf) == 7 and len(w) == len(rw) == 7
-    for a, b in zip(f, rf):
-        assert torch.equal(a, b)
+    for a, b in zip(f, rf):   # same predictor, two passes (cuDNN's default algorithms are not bitwise reproducible)
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, float(b.abs().max()))
+    for i, (a, b) in enumerate(zip(ofr.stn_warp_multi(list(rf), x[:, 1:2].contiguous()), rw)):
+        assert (a - b).abs().max().item() <= 1e-5, i      # the kernels on the reference pass's own flows
     for i, (a, b) in enumerate(zip(w, rw)):
-        assert (a - b).abs().max().item() <= 1e-5, i
-    assert s.shape == rs.shape == (2, 1, 256, 256) and g.shape == rg.shape
-    assert (g - rg).abs().max().item() <= 1e-5
+        assert (a - b).abs().max().item() <= 1e-4, i      # the wrapper's own pass (flows differ in the last bits)
+    assert s.shape == rs.shape == (1, 1, 256, 256) and g.shape == rg.shape
+    assert (g - rg).abs().max().item() <= 1e-4
     # labels: a sample within 1e-5 of a .5 boundary may round the other way; everything else must agree exactly
     pre = oracle.stn_warp(f[0].cpu(), segs[:, 1:2].cpu())
     safe = ((pre - pre.floor() - 0.5).abs() > 1e-4).to(DEV)
     assert torch.equal(s[safe], rs.to(s.dtype)[safe])
     assert float(s.min()) >= 0 and float(s.max()) <= 3 and torch.equal(s, s.round())
+    xb = synthetic_pairs(3, 256, seed=23).to(DEV)
+    with torch.no_grad():
+        fb, wb, sb, gb = ofr.OpticalFlowReg(net)(xb, segs.expand(3, 2, 256, 256).contiguous())
+    assert sb.shape == gb.shape == (3, 1, 256, 256) and len(wb) == 7
 
 
 def test_training_step_as_one_cuda_graph_matches_eager(ofr):
@@ -70,13 +78,35 @@ def test_training_step_as_one_cuda_graph_matches_eager(ofr):
     try:
         pair = synthetic_pairs(2, 128, seed=6).to(DEV)
         step, opt = build()
-        eager = [float(train_step(step, opt, pair)) for _ in range(6)]
-        step, opt = build()
         n0 = ofr.launch_count()
-        graphed = GraphedStep(step, opt, pair, warm_iters=3)   # 3 eager warm-up steps (they advance the weights), then capture
-        assert ofr.launch_count() - n0 >= 4 * 20              # the hot-path launches of the captured pass were recorded too
-        got = [float(graphed.replay()) for _ in range(3)]
-        np.testing.assert_allclose(got, eager[3:], rtol=2e-4)
+        graphed = GraphedStep(step, opt, pair, warm_iters=3)   # 3 eager warm-up steps, then the capture pass
+        assert ofr.launch_count() - n0 >= 4 * 20              # the hot-path launches were recorded into the graph too
+        params = [p for p in step.predictor.parameters() if p.requires_grad]
+        state = [t for p in params for t in opt.state[p].values() if torch.is_tensor(t)]
+        snap = [t.clone() for t in params + state]
+
+        def restore():
+            with torch.no_grad():
+                for t, v in zip(params + state, snap):
+                    t.copy_(v)
+
+        # one step from the SAME weights and optimizer state, eagerly and as a graph replay
+        loss_e = float(train_step(step, opt, pair))
+        after_e = [p.detach().clone() for p in params]
+        restore()
+        loss_g = float(graphed.replay())
+        after_g = [p.detach().clone() for p in params]
+        assert abs(loss_g - loss_e) <= 1e-5 * abs(loss_e), (loss_g, loss_e)
+        moved = sum(float((a - s_).abs().sum()) for a, s_ in zip(after_g, snap))
+        assert moved > 0                                       # the replay really stepped the optimizer
+        # Adam's first steps move every weight by ~lr whatever the gradient's size, so a gradient component whose sign
+        # is decided by rounding noise flips its update: compare the bulk, not the worst element
+        close_frac = sum(int(((a - b).abs() <= 2e-6).sum()) for a, b in zip(after_g, after_e)) / sum(p.numel() for p in params)
+        assert close_frac > 0.98, close_frac
+        # replays from the same state agree (cuDNN's default algorithms are not bitwise reproducible)
+        restore()
+        again = float(graphed.replay())
+        assert abs(again - loss_g) <= 1e-6 * abs(loss_g)
     finally:
         torch.backends.cudnn.benchmark = old
 
