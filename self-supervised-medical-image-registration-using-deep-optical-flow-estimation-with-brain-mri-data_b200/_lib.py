@@ -12,7 +12,9 @@ import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libofr_b200.so")
+# OFR_B200_LIB: development switch of the PYTHON loader (A/B runs of kernel variants built by tools/build_variant.py);
+# the library itself reads no environment variable
+LIB_PATH = os.environ.get("OFR_B200_LIB") or os.path.join(PKG_DIR, "libofr_b200.so")
 SOURCES = ["abi.cu", "channelnorm.cu", "resample2d.cu", "correlation.cu", "correlation_tma.cu", "correlation_umma.cu", "loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared"]
@@ -64,16 +66,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, jobs=None):
+def build(force=False, verbose=False, jobs=None, defines=(), out=None):
     """Compile every kernel for sm_100a into one shared library, in-tree (one nvcc per source file, in parallel, then
-    one link)."""
-    if not force and not needs_build():
+    one link).  ``defines`` / ``out``: build a variant (extra -D flags) into another file (tools/build_variant.py)."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     nvcc = _nvcc()
-    objdir = os.path.join(PKG_DIR, "build")
+    objdir = os.path.join(PKG_DIR, "build") if out is None else os.path.join(PKG_DIR, "build", os.path.basename(out) + ".d")
     os.makedirs(objdir, exist_ok=True)
-    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-D" + d for d in defines]
+    target = out or LIB_PATH
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
@@ -89,14 +92,14 @@ def build(force=False, verbose=False, jobs=None):
             print(res.stderr)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed compiling {src}:\n" + res.stderr[-4000:])
-    tmp = LIB_PATH + ".tmp"
+    tmp = target + ".tmp"
     cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + \
           [obj for _, obj, _, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed linking libofr_b200.so:\n" + res.stderr[-4000:])
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, target)
+    return target
 
 
 def _declare(lib):

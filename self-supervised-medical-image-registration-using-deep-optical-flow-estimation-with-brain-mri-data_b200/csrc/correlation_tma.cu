@@ -435,7 +435,10 @@ int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, 
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int kBM = 8;     // pixels per thread along x
+#ifndef OFR_BWD_BM
+#define OFR_BWD_BM 8
+#endif
+constexpr int kBM = OFR_BWD_BM;     // pixels per thread along x
 
 // CB channels per CTA = CG channel groups (warps) x CN channels per thread; the thread's channels are c = k*CG + cg.
 // TIC = x-displacements handled per register sweep (D must be a multiple of TIC).
@@ -487,12 +490,12 @@ __device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const fl
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < TIC; ++t) {
-            const float4 v0 = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP);
-            const float4 v1 = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + 4);
-            gv[t][0] = v0.x, gv[t][1] = v0.y, gv[t][2] = v0.z, gv[t][3] = v0.w;
-            gv[t][4] = v1.x, gv[t][5] = v1.y, gv[t][6] = v1.z, gv[t][7] = v1.w;
-        }
+        for (int t = 0; t < TIC; ++t)
+#pragma unroll
+            for (int i = 0; i < kBM; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + i);
+                gv[t][i] = v.x, gv[t][i + 1] = v.y, gv[t][i + 2] = v.z, gv[t][i + 3] = v.w;
+            }
     }
     constexpr int B0 = (T0 + T::XO) & ~3;                                // aligned start of the feature window
     constexpr int BL = ((T0 + T::XO + TIC + kBM - 1) - B0 + 3) / 4 * 4;  // floats to load
@@ -618,8 +621,9 @@ __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const
             if (c >= g.C) continue;
             float* o = gI + ((long long)b * g.C + c) * hw + (long long)y * g.W;
             if (xb + kBM <= g.W) {
-                __stcs(reinterpret_cast<float4*>(o + xb), make_float4(acc[0][k] * g.scale, acc[1][k] * g.scale, acc[2][k] * g.scale, acc[3][k] * g.scale));
-                __stcs(reinterpret_cast<float4*>(o + xb + 4), make_float4(acc[4][k] * g.scale, acc[5][k] * g.scale, acc[6][k] * g.scale, acc[7][k] * g.scale));
+#pragma unroll
+                for (int i = 0; i < kBM; i += 4)
+                    __stcs(reinterpret_cast<float4*>(o + xb + i), make_float4(acc[i][k] * g.scale, acc[i + 1][k] * g.scale, acc[i + 2][k] * g.scale, acc[i + 3][k] * g.scale));
             } else {
 #pragma unroll
                 for (int i = 0; i < kBM; ++i)
@@ -676,11 +680,11 @@ int dispatch_bwd4(const float* f1, const float* f2, const float* gO, float* gI1,
     // overlap the other's arithmetic
     // (16 x 32 tiles with 16 channels per CTA -- same shared memory, half the halo, twice the arithmetic per stage --
     // measured 8 % slower; a 3-deep ring at one CTA per SM 30 % slower.)
-    if (g.W > 16) return launch_bwd<4, 8, 4, 4, 9, 2, 32>(f1, f2, gO, gI1, gI2, g, st);
+    if (g.W > 16) return launch_bwd<4, 8, 32 / kBM, 4, 9, 2, 32>(f1, f2, gO, gI1, gI2, g, st);
     // small maps: the whole gradient tile (all 9 displacement rows) is in flight at once -- latency, not bandwidth --
     // and there are too few tiles to fill the machine, so the channels are spread over more warps (4 / 2 per thread)
-    if (g.W > 8) return launch_bwd<4, 8, 2, 8, 9, 9, 32>(f1, f2, gO, gI1, gI2, g, st);  // (16 groups: 21.6 -> 24.1 us)
-    return launch_bwd<4, 8, 1, 16, 9, 9, 32>(f1, f2, gO, gI1, gI2, g, st);
+    if (g.W > 8) return launch_bwd<4, 8, 16 / kBM, 8, 9, 9, 32>(f1, f2, gO, gI1, gI2, g, st);  // (16 groups: 21.6 -> 24.1 us)
+    return launch_bwd<4, 8, 8 / kBM, 16, 9, 9, 32>(f1, f2, gO, gI1, gI2, g, st);
 }
 
 bool applicable(const CorrGeom& g, int R, const void* a, const void* b, const void* c) {
@@ -738,7 +742,7 @@ int corr_bwd_tma(const float* f1, const float* f2, const float* gO, float* gI1, 
         }
         // R = 10 (class images of FlowNetC, 16 x 16 or 32 x 32): 8 x 16 tiles, 8 channel groups x 4 channels, 7
         // x-displacements per register sweep
-        return launch_bwd<10, 8, 2, 8, 7, 2, 32>(f1, f2, gO, gI1, gI2, g, st);
+        return launch_bwd<10, 8, 16 / kBM, 8, 7, 2, 32>(f1, f2, gO, gI1, gI2, g, st);
     }
     return OFR_ENOTSUP;
 }

@@ -82,6 +82,8 @@ CORR_CASES = {
     "pwc_l2": (1, 32, 64, 64, 4, 1, 4, 1, 1),
     "pwc_ragged": (2, 13, 12, 20, 4, 1, 4, 1, 1),      # C not a multiple of the chunk, H not of the tile
     "pwc_wide": (1, 8, 6, 136, 4, 1, 4, 1, 1),          # several x tiles with a ragged last one
+    "pwc_ragged_big": (3, 40, 50, 72, 4, 1, 4, 1, 1),    # 2 channel blocks (8 ragged), ragged last row tile and column strip
+    "pwc_tall": (2, 8, 200, 32, 4, 1, 4, 1, 1),           # 25 row tiles of one column strip
     "flownetc": (1, 256, 32, 32, 20, 1, 20, 1, 2),
     "flownetc_small": (2, 20, 12, 16, 20, 1, 20, 1, 2),
     "flownetc_tc": (2, 48, 32, 64, 20, 1, 20, 1, 2),    # class images 16 x 32: tensor-core forward, 2 x 2 tiles, 3 K stages
@@ -226,6 +228,36 @@ def test_correlation_is_reproducible_and_skips_unneeded_grads(ofr):
     (g,) = torch.autograd.grad(o1.sum(), f1)
     (g2,) = torch.autograd.grad(o2.sum(), f1)
     assert torch.equal(g, g2)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_correlation_backward_single_gradient_many_tiles(ofr, which):
+    """PWC backward with only ONE gradient requested (the launch then holds one direction) on a batch with far more tiles
+    than SMs (B = 40, 32 channels, 48 x 64): against the definition accumulated in float64 on the GPU, and bit-identical
+    run to run."""
+    B, C, H, W = 40, 32, 48, 64
+    f1 = torch.randn(B, C, H, W, generator=gen(130)).to(DEV)
+    f2 = torch.randn(B, C, H, W, generator=gen(131)).to(DEV)
+    go = torch.randn(B, 81, H, W, generator=gen(132)).to(DEV)
+    xs = [f1.clone().requires_grad_(which == 0), f2.clone().requires_grad_(which == 1)]
+    corr = ofr.Correlation(4, 1, 4, 1, 1, 1)
+    (g,) = torch.autograd.grad(corr(*xs), xs[which], go)
+    (g2,) = torch.autograd.grad(corr(*xs), xs[which], go)
+    assert torch.equal(g, g2)
+    # float64 definition on the GPU
+    pad = torch.nn.functional.pad
+    a, b, gd = f1.double(), f2.double(), go.double()
+    ref = torch.zeros(B, C, H + 8, W + 8, dtype=torch.float64, device=DEV) if which == 1 else torch.zeros(B, C, H, W, dtype=torch.float64, device=DEV)
+    bp = pad(b, (4, 4, 4, 4))
+    for tj in range(9):
+        for ti in range(9):
+            gp = gd[:, tj * 9 + ti].unsqueeze(1)
+            if which == 0:
+                ref += gp * bp[:, :, tj:tj + H, ti:ti + W]
+            else:
+                ref[:, :, tj:tj + H, ti:ti + W] += gp * a
+    ref = (ref if which == 0 else ref[:, :, 4:4 + H, 4:4 + W]) / C
+    close(g, ref, atol=1e-7, rtol=1e-4, what=f"single-gradient backward grad[{which}]")
 
 
 def test_spatial_correlation_sample_alias(ofr):
@@ -682,7 +714,7 @@ class _Guarded:
         assert bool((lo == self.sentinel).all()) and bool((hi == self.sentinel).all()), f"{what}: guard zone overwritten"
 
 
-@pytest.mark.parametrize("shape", [(2, 13, 12, 20), (1, 8, 6, 136), (2, 196, 4, 4), (3, 40, 16, 16), (1, 32, 30, 36)])
+@pytest.mark.parametrize("shape", [(2, 13, 12, 20), (1, 8, 6, 136), (2, 196, 4, 4), (3, 40, 16, 16), (1, 32, 30, 36), (2, 33, 50, 72)])
 def test_correlation_writes_stay_inside_their_buffers(ofr, shape):
     """Raw C-ABI calls with guard zones around every written buffer (TMA kernels, cluster split, ragged tiles)."""
     import ctypes
