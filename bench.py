@@ -374,8 +374,16 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # leave without tearing the communicator down: destroying it while a captured graph still references its
+        # collectives hung the process at exit (measured at N = 2); the JSON line is out, every rank is past its last
+        # collective
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        del graphed
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
