@@ -251,9 +251,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    per_rank = {}
+
+    def max_over_ranks(ms, tag=None):
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         if world > 1:
+            if tag is not None:  # every rank's own device time for the region (the reported time is their maximum)
+                every = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(every, t)
+                per_rank[tag] = [round(float(e.item()), 3) for e in every]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
@@ -272,7 +278,7 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = ofr.launch_count() - n0
-    eager_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    eager_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, "eager_ms_per_step")
 
     # ---- timed region 1b: the same step as one CUDA graph
     graphed, graph_ms, graph_err = None, None, None
@@ -287,7 +293,7 @@ def run_ours(args):
                 graphed.replay()
             e1.record()
             barrier()
-            graph_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+            graph_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, "cuda_graph_ms_per_step")
         except Exception as ex:  # capture refused (it never silently changes the workload): report and keep eager
             graphed, graph_err = None, f"{type(ex).__name__}: {str(ex)[:200]}"
             torch.cuda.synchronize()
@@ -366,7 +372,8 @@ def run_ours(args):
                        "loss": "fused stn + OFEloss (ofr_regloss_fwd/bwd)" if args.fused_loss else "stn_multi then OFEloss",
                        "l2": "working set (activations > 1 GB per step) exceeds the 126 MB L2; no explicit flush"},
             "step_modes": {"eager_ms_per_step": eager_ms, "cuda_graph_ms_per_step": graph_ms, "cuda_graph_error": graph_err,
-                           "headline": "cuda_graph" if headline_graph else "eager"},
+                           "headline": "cuda_graph" if headline_graph else "eager",
+                           "per_rank_ms_per_step": per_rank or None},
             "roofline": roofline, "kernels": rows[:24], "secondary": secondary, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pair_host.numel() * 4 * world,
                     "d2h_bytes_per_step": 8 * world, "last_loss": last, "ms_per_step": e2e_ms},

@@ -287,12 +287,19 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 4) loss_partial_kernel(c
     float mm[4] = {3.0e38f, -3.0e38f, 3.0e38f, -3.0e38f};
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k] = 0.0;
-    for (int item = c0; item < p.sc[s].items; item += nc) {  // one item per CTA unless strips * B > kMaxCtasPerScale
+    auto run = [&](int item) {
         const Strip st = strip_of_item(p, s, item);
         if (p.sc[s].vec4)
             partial_body<4, FUSED>(p, st, mm, acc);
         else
             partial_body<1, FUSED>(p, st, mm, acc);
+    };
+    // one item per CTA (straight-line code: the loop form costs 7-15 % here) unless strips * B > kMaxCtasPerScale
+    if (p.sc[s].items <= nc) {
+        run(c0);
+    } else {
+#pragma unroll 1
+        for (int item = c0; item < p.sc[s].items; item += nc) run(item);
     }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -610,12 +617,18 @@ __global__ void __launch_bounds__(kThreads) loss_bwd_kernel(const __grid_constan
     const int s = scale_of_cta(p, blockIdx.x);
     const int c0 = blockIdx.x - p.cta_begin[s], nc = p.cta_begin[s + 1] - p.cta_begin[s];
     const BwdCoef c = bwd_coef(p, s, grad4, state);
-    for (int item = c0; item < p.sc[s].items; item += nc) {
+    auto run = [&](int item) {
         const Strip st = strip_of_item(p, s, item);
         if (p.sc[s].vec4)
             bwd_body<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
         else
             bwd_body<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    };
+    if (p.sc[s].items <= nc) {
+        run(c0);
+    } else {
+#pragma unroll 1
+        for (int item = c0; item < p.sc[s].items; item += nc) run(item);
     }
 }
 
@@ -625,12 +638,18 @@ __global__ void __launch_bounds__(kThreads, 2) regloss_bwd_kernel(const __grid_c
     const int s = scale_of_cta(p, blockIdx.x);
     const int c0 = blockIdx.x - p.cta_begin[s], nc = p.cta_begin[s + 1] - p.cta_begin[s];
     const BwdCoef c = bwd_coef(p, s, grad4, state);
-    for (int item = c0; item < p.sc[s].items; item += nc) {
+    auto run = [&](int item) {
         const Strip st = strip_of_item(p, s, item);
         if (p.sc[s].vec4)
             bwd_body_fused<4>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
         else
             bwd_body_fused<1>(p, st, c.cp, c.cs, c.k1, c.k2, c.mf, c.mw);
+    };
+    if (p.sc[s].items <= nc) {
+        run(c0);
+    } else {
+#pragma unroll 1
+        for (int item = c0; item < p.sc[s].items; item += nc) run(item);
     }
 }
 

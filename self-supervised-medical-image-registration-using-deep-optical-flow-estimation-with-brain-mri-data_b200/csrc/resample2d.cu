@@ -173,6 +173,15 @@ __device__ __forceinline__ void warp_fwd_body_lean(const float* __restrict__ in1
 }
 
 
+// Cross-CTA L2 prefetch (flow-gradient kernel only).  A thread's work is a chain of dependent DRAM round trips (flow ->
+// tap addresses -> image), and with ~1000 resident threads per SM of four pixels each the kernels are bound by that
+// latency (ncu: long_scoreboard 5.6 per issue at ~50 % of the HBM peak).  The CTA that handles image b pulls the rows image
+// b + pf_z will need -- same (x, y) position, about 1.5 waves of CTAs further in launch order -- into the L2: one
+// `prefetch.global.L2` per 128-byte row segment (lane 0 of each warp).  Measured (B = 24, 512 x 512, one channel):
+// flow-gradient kernel 53.7 -> 49.8 us; the FORWARD kernel got slower with it (29.1 -> 34.8 us, PWC level 2 33.5 ->
+// 40.2 us: its own loads then queue behind the prefetches), so it does not use it.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int MODE, bool LEAN>
 __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const float* __restrict__ in1,
                                                                       const float* __restrict__ flow,
@@ -253,10 +262,26 @@ __global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const
                                                                            const float* __restrict__ flow,
                                                                            const float* __restrict__ gO,
                                                                            float* __restrict__ gI2, WarpGeom g,
-                                                                           float sx, float sy) {
+                                                                           float sx, float sy, int pf_z) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * kPX;
     if (x >= g.Wf || y0 >= g.Hf) return;
+#ifndef OFR_NO_XPF
+    if (pf_z > 0 && blockDim.x == 32 && threadIdx.x == 0 && (int)blockIdx.z + pf_z < g.B && g.C <= 8) {  // (see resample_fwd_kernel)
+        const int bp = blockIdx.z + pf_z, hwf = g.Hf * g.Wf, hwi = g.Hin * g.Win;
+        const bool same = g.Hin == g.Hf && g.Win == g.Wf;
+#pragma unroll
+        for (int k = 0; k < kPX; ++k) {
+            const int ro = min(y0 + k, g.Hf - 1) * g.Wf + x;
+            prefetch_l2(flow + (size_t)bp * 2 * hwf + ro);
+            prefetch_l2(flow + (size_t)bp * 2 * hwf + hwf + ro);
+            for (int c = 0; c < g.C; ++c) {
+                prefetch_l2(gO + ((size_t)bp * g.C + c) * hwf + ro);
+                if (same) prefetch_l2(in1 + ((size_t)bp * g.C + c) * hwi + ro);
+            }
+        }
+    }
+#endif
     for (int b = blockIdx.z; b < g.B; b += gridDim.z) warp_bwd_flow_body<MODE>(in1, flow, gO, gI2, g, sx, sy, x, y0, b);
 }
 
@@ -730,6 +755,13 @@ WarpGeom make_geom(int B, int C, int Hin, int Win, int Hf, int Wf, float fs) {
 
 // (bx, by) with bx * by = 256 threads: bx = the smallest power of two covering a row, at most 32 (one warp = whole runs
 // of consecutive pixels); a CTA covers by * kPX rows
+// slices ahead (in blockIdx.z) whose rows a CTA pulls into the L2: about 1.5 waves of resident CTAs further in launch order
+int prefetch_distance(const dim3& grid, int ctas_per_sm) {
+    const long long per_z = (long long)grid.x * grid.y;
+    const long long ahead = (3ll * ofr::sm_count() * ctas_per_sm / 2 + per_z - 1) / per_z;
+    return (int)(ahead < 1 ? 1 : ahead);
+}
+
 void block_shape(int W, int H, dim3& block, dim3& grid, unsigned gz) {
     int bx = 8;
     while (bx < W && bx < 32) bx <<= 1;
@@ -759,7 +791,7 @@ int launch_flow_only(const float* in1, const float* flow, const float* gO, float
                      float sy, cudaStream_t st) {
     dim3 block, grid;
     block_shape(g.Wf, g.Hf, block, grid, (unsigned)g.B);
-    resample_bwd_flow_kernel<MODE><<<grid, block, 0, st>>>(in1, flow, gO, gI2, g, sx, sy);
+    resample_bwd_flow_kernel<MODE><<<grid, block, 0, st>>>(in1, flow, gO, gI2, g, sx, sy, prefetch_distance(grid, 3));
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }

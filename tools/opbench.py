@@ -170,6 +170,21 @@ def cases(B, S, only=".*", dry=False):
                     lambda: (keep, L.ofr_regloss_bwd(P(fixed), B, S, S, arr, n, 0.5, 100.0, 100.0, P(g4), P(state),
                                                      stream()))[1]))
 
+    def copy(mb):
+        # reference point: what a plain elementwise ATen kernel (b = a + 1, 128-bit vectorised) moving the same bytes reaches
+        # against the 1 GiB-copy peak (`b.copy_(a)` would go through the copy engine, not an SM kernel)
+        name = f"torch_add {mb}MB"
+        if dry:
+            out.append((name, 0, 0, None))
+            return
+        if not want(name):
+            return
+        a = torch.empty(mb * 250000 // 2, device=DEV)
+        bb = torch.empty_like(a)
+        out.append((name, 2 * a.numel() * 4, 0, lambda: (torch.add(a, 1.0, out=bb), 0)[1]))
+
+    for mb in (50, 100, 150):
+        copy(mb)
     # PWC-Net pyramid (PWCNet.py:200-259): levels 2..6
     for lvl, C in [(2, 32), (3, 64), (4, 96), (5, 128), (6, 196)]:
         corr(f"pwc_l{lvl}", C, S >> lvl, 4, 4, 1)
