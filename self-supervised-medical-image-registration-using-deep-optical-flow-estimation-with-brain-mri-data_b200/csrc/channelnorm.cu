@@ -47,98 +47,116 @@ struct Pix<1> {
 constexpr int kVPT = 4;  // vectors per thread: their loads are all issued before the first use (bytes in flight per SM
                          // = resident threads x kVPT x 16 B; one vector per thread left the HBM pipe half empty)
 
-// thread -> vectors (blockIdx.x * kVPT + j) * kThreads + threadIdx.x, j < kVPT: every load / store of a warp is one
-// contiguous 512-byte run
+// blockIdx.y = image, thread -> vectors (blockIdx.x * kVPT + j) * kThreads + threadIdx.x of that image, j < kVPT: every
+// load / store of a warp is one contiguous 512-byte run.  What made the first version slow (tools/micro/stream_variants.cu,
+// 50 MB one-channel forward under back-to-back launches: 12.9 us against 9.5 us for the same loads and stores without
+// them): (i) a flat index split by 64-bit divisions in front of the first load (-1.6 us without), (ii) a run-time channel
+// loop around PREDICATED loads, which the compiler serialises behind branches (-1.5 us with the channel count a template
+// constant or the loads unpredicated).  So: no division (2-D grid), CC = compile-time channel count for the model's
+// C = 1, 2, 3 (0 = run-time loop), and tail vectors are loaded from a clamped (valid) index -- only the stores are
+// predicated.
 // x2 != nullptr: the norm of the difference x - x2 (`x1 - resample(...)` then ChannelNorm at flownet2/models.py:140-141,
 // 152-153, 166-167, 179-180) without materialising the difference
-template <int VEC, bool DIFF>
+template <int VEC, bool DIFF, int CC>
 __global__ void __launch_bounds__(kThreads) chnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x2,
-                                                              float* __restrict__ out, int C, long long hw,
-                                                              long long total_vec) {
+                                                              float* __restrict__ out, int Crt, long long hw, int B) {
+    const int C = CC ? CC : Crt;
     const long long hwv = hw / VEC;
     const long long i0 = (long long)blockIdx.x * kVPT * kThreads + threadIdx.x;
-    const float* xp[kVPT];
-    float* op[kVPT];
+    long long p[kVPT];
     bool ok[kVPT];
 #pragma unroll
     for (int j = 0; j < kVPT; ++j) {
         const long long i = i0 + (long long)j * kThreads;
-        ok[j] = i < total_vec;
-        const long long ic = ok[j] ? i : 0;
-        const long long b = ic / hwv, p = (ic - b * hwv) * VEC;
-        xp[j] = x + b * C * hw + p;
-        op[j] = out + b * hw + p;
+        ok[j] = i < hwv;
+        p[j] = (ok[j] ? i : hwv - 1) * VEC;
     }
     const long long d2 = DIFF ? x2 - x : 0;  // element distance between the two inputs
-    typename Pix<VEC>::T s[kVPT];
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float* xb = x + (long long)b * C * hw;
+        typename Pix<VEC>::T s[kVPT];
 #pragma unroll
-    for (int j = 0; j < kVPT; ++j) s[j] = Pix<VEC>::zero();
-    for (int c = 0; c < C; ++c) {
-        typename Pix<VEC>::T v[kVPT];
+        for (int j = 0; j < kVPT; ++j) s[j] = Pix<VEC>::zero();
 #pragma unroll
-        for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
-        if (DIFF) {
+        for (int c = 0; c < (CC ? CC : 1); ++c) {       // CC > 0: unrolled; CC == 0: one pass of the run-time loop below
+            for (int cr = 0; cr < (CC ? 1 : C); ++cr) {
+                const float* xc = xb + (long long)(CC ? c : cr) * hw;
+                typename Pix<VEC>::T v[kVPT];
 #pragma unroll
-            for (int j = 0; j < kVPT; ++j)
-                if (ok[j]) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xp[j] + d2));
+                for (int j = 0; j < kVPT; ++j) v[j] = Pix<VEC>::ld(xc + p[j]);
+                if (DIFF) {
+#pragma unroll
+                    for (int j = 0; j < kVPT; ++j) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xc + p[j] + d2));
+                }
+#pragma unroll
+                for (int j = 0; j < kVPT; ++j) s[j] = Pix<VEC>::fma(v[j], v[j], s[j]);
+            }
         }
+        float* ob = out + (long long)b * hw;
 #pragma unroll
-        for (int j = 0; j < kVPT; ++j) {
-            s[j] = Pix<VEC>::fma(v[j], v[j], s[j]);
-            xp[j] += hw;
-        }
+        for (int j = 0; j < kVPT; ++j)
+            if (ok[j]) Pix<VEC>::st(ob + p[j], Pix<VEC>::sqrt(s[j]));
     }
-#pragma unroll
-    for (int j = 0; j < kVPT; ++j)
-        if (ok[j]) Pix<VEC>::st(op[j], Pix<VEC>::sqrt(s[j]));
 }
 
 // x2 != nullptr: backward of the norm of x - x2; gI gets the gradient of x, gI2 (optional) its negative for x2
-template <int VEC, bool DIFF>
+template <int VEC, bool DIFF, int CC>
 __global__ void __launch_bounds__(kThreads) chnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x2,
                                                               const float* __restrict__ out,
                                                               const float* __restrict__ gO, float* __restrict__ gI,
-                                                              float* __restrict__ gI2, int C, long long hw,
-                                                              long long total_vec) {
+                                                              float* __restrict__ gI2, int Crt, long long hw, int B) {
+    const int C = CC ? CC : Crt;
     const long long hwv = hw / VEC;
     const long long i0 = (long long)blockIdx.x * kVPT * kThreads + threadIdx.x;
-    const float* xp[kVPT];
-    float* gp[kVPT];
+    long long p[kVPT];
     bool ok[kVPT];
-    typename Pix<VEC>::T r[kVPT];  // gO / (out + 1e-8), one division per pixel instead of per element
 #pragma unroll
     for (int j = 0; j < kVPT; ++j) {
         const long long i = i0 + (long long)j * kThreads;
-        ok[j] = i < total_vec;
-        const long long ic = ok[j] ? i : 0;
-        const long long b = ic / hwv, p = (ic - b * hwv) * VEC;
-        xp[j] = x + b * C * hw + p;
-        gp[j] = (DIFF && !gI) ? gI2 + b * C * hw + p : gI + b * C * hw + p;  // DIFF: gI and / or gI2
-        r[j] = Pix<VEC>::ratio(Pix<VEC>::ld(gO + b * hw + p), Pix<VEC>::ld(out + b * hw + p));
+        ok[j] = i < hwv;
+        p[j] = (ok[j] ? i : hwv - 1) * VEC;
     }
-    const long long d2 = DIFF ? x2 - x : 0, dg = (DIFF && gI && gI2) ? gI2 - gI : 0;
-    for (int c = 0; c < C; ++c) {
-        typename Pix<VEC>::T v[kVPT];
+    const long long d2 = DIFF ? x2 - x : 0;
+    float* g1 = (DIFF && !gI) ? gI2 : gI;                       // DIFF: gI and / or gI2
+    const bool both = DIFF && gI && gI2;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        typename Pix<VEC>::T r[kVPT];  // gO / (out + 1e-8), one division per pixel instead of per element
 #pragma unroll
-        for (int j = 0; j < kVPT; ++j) v[j] = ok[j] ? Pix<VEC>::ld(xp[j]) : Pix<VEC>::zero();
-        if (DIFF) {
+        for (int j = 0; j < kVPT; ++j)
+            r[j] = Pix<VEC>::ratio(Pix<VEC>::ld(gO + (long long)b * hw + p[j]), Pix<VEC>::ld(out + (long long)b * hw + p[j]));
+        const long long base = (long long)b * C * hw;
 #pragma unroll
-            for (int j = 0; j < kVPT; ++j)
-                if (ok[j]) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(xp[j] + d2));
-        }
+        for (int c = 0; c < (CC ? CC : 1); ++c) {
+            for (int cr = 0; cr < (CC ? 1 : C); ++cr) {
+                const long long off = base + (long long)(CC ? c : cr) * hw;
+                typename Pix<VEC>::T v[kVPT];
 #pragma unroll
-        for (int j = 0; j < kVPT; ++j) {
-            const typename Pix<VEC>::T gq = Pix<VEC>::mul(v[j], r[j]);
-            if (!DIFF) {
-                if (ok[j]) Pix<VEC>::st(gp[j], gq);
-            } else if (ok[j]) {
-                if (gI) Pix<VEC>::st(gp[j], gq);
-                if (gI2) Pix<VEC>::st(gI ? gp[j] + dg : gp[j], Pix<VEC>::neg(gq));
+                for (int j = 0; j < kVPT; ++j) v[j] = Pix<VEC>::ld(x + off + p[j]);
+                if (DIFF) {
+#pragma unroll
+                    for (int j = 0; j < kVPT; ++j) v[j] = Pix<VEC>::sub(v[j], Pix<VEC>::ld(x + off + p[j] + d2));
+                }
+#pragma unroll
+                for (int j = 0; j < kVPT; ++j) {
+                    const typename Pix<VEC>::T gq = Pix<VEC>::mul(v[j], r[j]);
+                    if (ok[j]) {
+                        if (!DIFF) {
+                            Pix<VEC>::st(gI + off + p[j], gq);
+                        } else {
+                            Pix<VEC>::st(g1 + off + p[j], (gI ? gq : Pix<VEC>::neg(gq)));
+                            if (both) Pix<VEC>::st(gI2 + off + p[j], Pix<VEC>::neg(gq));
+                        }
+                    }
+                }
             }
-            xp[j] += hw;
-            gp[j] += hw;
         }
     }
+}
+
+// x: vectors of one image / (kThreads * kVPT); y: images (a CTA walks several when B exceeds the grid limit)
+dim3 grid_for_image(long long vec_per_image, int B) {
+    const long long gx = (vec_per_image + kThreads * kVPT - 1) / (kThreads * kVPT);
+    return dim3((unsigned)gx, (unsigned)(B < 65535 ? B : 65535));
 }
 
 }  // namespace
@@ -152,15 +170,21 @@ extern "C" int ofr_chnorm_diff_fwd(const float* x, const float* x2, float* out, 
     if (!x || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return OFR_EINVAL;
     const long long hw = (long long)H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    if (hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && (!x2 || ofr::aligned16(x2))) {
-        const long long n = (long long)B * hw / 4;
-        if (x2) chnorm_fwd_kernel<4, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
-        else chnorm_fwd_kernel<4, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
+    const bool v4 = hw % 4 == 0 && ofr::aligned16(x) && ofr::aligned16(out) && (!x2 || ofr::aligned16(x2));
+    const dim3 grid = grid_for_image(v4 ? hw / 4 : hw, B);
+#define OFR_CHN_FWD(VEC, DIFF, CC) chnorm_fwd_kernel<VEC, DIFF, CC><<<grid, kThreads, 0, st>>>(x, x2, out, C, hw, B)
+#define OFR_CHN_FWD_C(VEC, DIFF)                                                                          \
+    do {                                                                                                  \
+        if (C == 1) OFR_CHN_FWD(VEC, DIFF, 1); else if (C == 2) OFR_CHN_FWD(VEC, DIFF, 2);                \
+        else if (C == 3) OFR_CHN_FWD(VEC, DIFF, 3); else OFR_CHN_FWD(VEC, DIFF, 0);                       \
+    } while (0)
+    if (v4) {
+        if (x2) OFR_CHN_FWD_C(4, true); else OFR_CHN_FWD_C(4, false);
     } else {
-        const long long n = (long long)B * hw;
-        if (x2) chnorm_fwd_kernel<1, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
-        else chnorm_fwd_kernel<1, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, C, hw, n);
+        if (x2) OFR_CHN_FWD(1, true, 0); else OFR_CHN_FWD(1, false, 0);
     }
+#undef OFR_CHN_FWD_C
+#undef OFR_CHN_FWD
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
@@ -178,15 +202,21 @@ extern "C" int ofr_chnorm_diff_bwd(const float* x, const float* x2, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const bool al = ofr::aligned16(x) && ofr::aligned16(out) && ofr::aligned16(gO) && (!gI || ofr::aligned16(gI)) &&
                     (!gI2 || ofr::aligned16(gI2)) && (!x2 || ofr::aligned16(x2));
-    if (hw % 4 == 0 && al) {
-        const long long n = (long long)B * hw / 4;
-        if (x2) chnorm_bwd_kernel<4, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
-        else chnorm_bwd_kernel<4, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
+    const bool v4 = hw % 4 == 0 && al;
+    const dim3 grid = grid_for_image(v4 ? hw / 4 : hw, B);
+#define OFR_CHN_BWD(VEC, DIFF, CC) chnorm_bwd_kernel<VEC, DIFF, CC><<<grid, kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, B)
+#define OFR_CHN_BWD_C(VEC, DIFF)                                                                          \
+    do {                                                                                                  \
+        if (C == 1) OFR_CHN_BWD(VEC, DIFF, 1); else if (C == 2) OFR_CHN_BWD(VEC, DIFF, 2);                \
+        else if (C == 3) OFR_CHN_BWD(VEC, DIFF, 3); else OFR_CHN_BWD(VEC, DIFF, 0);                       \
+    } while (0)
+    if (v4) {
+        if (x2) OFR_CHN_BWD_C(4, true); else OFR_CHN_BWD_C(4, false);
     } else {
-        const long long n = (long long)B * hw;
-        if (x2) chnorm_bwd_kernel<1, true><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
-        else chnorm_bwd_kernel<1, false><<<(unsigned)((n + kThreads * kVPT - 1) / (kThreads * kVPT)), kThreads, 0, st>>>(x, x2, out, gO, gI, gI2, C, hw, n);
+        if (x2) OFR_CHN_BWD(1, true, 0); else OFR_CHN_BWD(1, false, 0);
     }
+#undef OFR_CHN_BWD_C
+#undef OFR_CHN_BWD
     OFR_LAUNCH_CHECK();
     return OFR_OK;
 }
