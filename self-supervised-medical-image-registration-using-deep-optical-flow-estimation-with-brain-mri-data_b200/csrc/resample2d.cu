@@ -99,6 +99,7 @@ __device__ __forceinline__ void warp_fwd_body(const float* __restrict__ in1, con
         }
         const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
         float* o = out + ((size_t)b * g.C + c0) * hwf + rem;
+        // (a compile-time trip count of kFwdChunk with 4 channels unrolled spills at 64 registers: 33.5 -> 135 us at level 2)
 #pragma unroll 2
         for (int c = c0; c < c1; ++c, img = img + hwi, o = o + hwf) {
             float r[kPX];
@@ -206,7 +207,9 @@ __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const floa
 // ------------------------------------------------------------------------------------------------ backward: flow only
 // gI2 only (the image needs no gradient: opticalFlowReg.stn on the moving image, FlowNet2's Resample2d on the input
 // images).  Same thread mapping as the forward; channels looped in the thread.
-template <int MODE>
+// CC: compile-time channel count (1: the one-channel images of stn / FlowNet2's Resample2d -- a run-time channel loop
+// around predicated gathers is serialised behind branches, tools/micro/stream_variants.cu); 0 = run-time loop
+template <int MODE, int CC = 0>
 __device__ __forceinline__ void warp_bwd_flow_body(const float* __restrict__ in1, const float* __restrict__ flow,
                                                    const float* __restrict__ gO, float* __restrict__ gI2,
                                                    const WarpGeom& g, float sx, float sy, int x, int y0, int b) {
@@ -234,9 +237,11 @@ __device__ __forceinline__ void warp_bwd_flow_body(const float* __restrict__ in1
         float ax[kPX], ay[kPX];
 #pragma unroll
         for (int k = 0; k < kPX; ++k) ax[k] = ay[k] = 0.f;
-        const float* img = in1 + (size_t)b * g.C * hwi;
-        const float* gp = gO + (size_t)b * g.C * hwf + rem;
-        for (int c = 0; c < g.C; ++c, img = img + hwi, gp = gp + hwf) {
+        const int nc = CC ? CC : g.C;
+        const float* img = in1 + (size_t)b * nc * hwi;
+        const float* gp = gO + (size_t)b * nc * hwf + rem;
+#pragma unroll
+        for (int c = 0; c < nc; ++c, img = img + hwi, gp = gp + hwf) {
 #pragma unroll
             for (int k = 0; k < kPX; ++k) {
                 const float go = ok[k] ? __ldg(gp + k * g.Wf) : 0.f;
@@ -282,7 +287,11 @@ __global__ void __launch_bounds__(kFwdThreads, 3) resample_bwd_flow_kernel(const
         }
     }
 #endif
-    for (int b = blockIdx.z; b < g.B; b += gridDim.z) warp_bwd_flow_body<MODE>(in1, flow, gO, gI2, g, sx, sy, x, y0, b);
+    if (g.C == 1) {
+        for (int b = blockIdx.z; b < g.B; b += gridDim.z) warp_bwd_flow_body<MODE, 1>(in1, flow, gO, gI2, g, sx, sy, x, y0, b);
+    } else {
+        for (int b = blockIdx.z; b < g.B; b += gridDim.z) warp_bwd_flow_body<MODE, 0>(in1, flow, gO, gI2, g, sx, sy, x, y0, b);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ multi-scale stn
@@ -318,7 +327,10 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stn_multi_kernel(const __grid_
     const int y0 = (ty * (kFwdThreads / 32) + (threadIdx.x >> 5)) * kPX;
     if (x >= sc.g.Wf || y0 >= sc.g.Hf) return;
     if (BACKWARD)
-        warp_bwd_flow_body<OFR_WARP_STN>(sc.frame, sc.flow, sc.g_out, sc.g_flow, sc.g, sc.sx, sc.sy, x, y0, b);
+        if (sc.g.C == 1)
+            warp_bwd_flow_body<OFR_WARP_STN, 1>(sc.frame, sc.flow, sc.g_out, sc.g_flow, sc.g, sc.sx, sc.sy, x, y0, b);
+        else
+            warp_bwd_flow_body<OFR_WARP_STN, 0>(sc.frame, sc.flow, sc.g_out, sc.g_flow, sc.g, sc.sx, sc.sy, x, y0, b);
     else
         warp_fwd_body_lean<OFR_WARP_STN>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, sc.g.C);
 }
