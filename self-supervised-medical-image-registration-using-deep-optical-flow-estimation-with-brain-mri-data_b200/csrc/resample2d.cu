@@ -123,7 +123,8 @@ __device__ __forceinline__ void warp_fwd_body(const float* __restrict__ in1, con
 }
 
 
-template <int MODE>
+// ONE: exactly one channel (stn of the moving image, FlowNet2's Resample2d): no channel loop at all
+template <int MODE, bool ONE = false>
 __device__ __forceinline__ void warp_fwd_body_lean(const float* __restrict__ in1, const float* __restrict__ flow,
                                               float* __restrict__ out, const WarpGeom& g, int x, int y0, int b, int c0,
                                               int c1) {
@@ -157,7 +158,7 @@ __device__ __forceinline__ void warp_fwd_body_lean(const float* __restrict__ in1
     const float* img = opaque_ptr(in1 + ((size_t)b * g.C + c0) * hwi);
     float* o = opaque_ptr(out + ((size_t)b * g.C + c0) * hwf);
 #pragma unroll 2
-    for (int c = c0; c < c1; ++c, img = opaque_ptr(img + hwi), o = opaque_ptr(o + hwf)) {
+    for (int c = c0; c < (ONE ? c0 + 1 : c1); ++c, img = opaque_ptr(img + hwi), o = opaque_ptr(o + hwf)) {
         float r[kPX];
 #pragma unroll
         for (int k = 0; k < kPX; ++k) {
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(kFwdThreads, 4) resample_fwd_kernel(const floa
             chunk = z - b * nchunks;
         }
         const int c0 = chunk * kFwdChunk;
-        if (LEAN)
+        if (LEAN && g.C == 1)
+            warp_fwd_body_lean<MODE, true>(in1, flow, out, g, x, y0, b, 0, 1);
+        else if (LEAN)
             warp_fwd_body_lean<MODE>(in1, flow, out, g, x, y0, b, c0, min(c0 + kFwdChunk, g.C));
         else
             warp_fwd_body<MODE>(in1, flow, out, g, x, y0, b, c0, min(c0 + kFwdChunk, g.C));
@@ -332,7 +335,10 @@ __global__ void __launch_bounds__(kFwdThreads, 3) stn_multi_kernel(const __grid_
         else
             warp_bwd_flow_body<OFR_WARP_STN, 0>(sc.frame, sc.flow, sc.g_out, sc.g_flow, sc.g, sc.sx, sc.sy, x, y0, b);
     else
-        warp_fwd_body_lean<OFR_WARP_STN>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, sc.g.C);
+        if (sc.g.C == 1)
+            warp_fwd_body_lean<OFR_WARP_STN, true>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, 1);
+        else
+            warp_fwd_body_lean<OFR_WARP_STN>(sc.frame, sc.flow, sc.out, sc.g, x, y0, b, 0, sc.g.C);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: image (+ flow)

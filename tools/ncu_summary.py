@@ -1,21 +1,49 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (via `ncu -i ... --page raw --csv`) into a compact per-kernel table with stall reasons."""
-import csv, subprocess, sys, io
-rep = sys.argv[1]
-txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(txt)))
-hdr, units, data = rows[0], rows[1], rows[2:]
-col = {h: i for i, h in enumerate(hdr)}
-stall = [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio')]
-def f(r, k):
-    try: return float(r[col[k]].replace(',', ''))
-    except Exception: return float('nan')
-for r in data:
-    name = r[col['Kernel Name']]
-    name = name.replace('void ', '').replace('<unnamed>::', '')[:70]
-    print(f"## {name}  grid={r[col['Grid Size']]} block={r[col['Block Size']]}")
-    print(f"   dur {f(r,'gpu__time_duration.sum'):.1f} {units[col['gpu__time_duration.sum']]} | dram R {f(r,'dram__bytes_read.sum'):.1f} W {f(r,'dram__bytes_write.sum'):.1f} {units[col['dram__bytes_read.sum']]} | regs {r[col['launch__registers_per_thread']]} | "
-          f"occupancy {f(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):.0f}% | issue {f(r,'smsp__issue_active.avg.pct_of_peak_sustained_active'):.0f}% | fma pipe {f(r,'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'):.0f}% | "
-          f"smem wavefronts {f(r,'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum')/1e6:.2f}M (conflicts {f(r,'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum')/1e6:.2f}M) | cycles {f(r,'sm__cycles_elapsed.avg')/1e3:.1f}K | eligible/cyc {f(r,'smsp__warps_eligible.avg.per_cycle_active'):.2f}")
-    vals = sorted(((f(r, h), h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]) for h in stall), reverse=True)
-    print("   stalls/issue: " + ", ".join(f"{h} {v:.2f}" for v, h in vals[:6]))
+"""One-paragraph summary per kernel launch of an .ncu-rep (`ncu --set full`), the numbers DESIGN.md quotes.
+
+    python tools/ncu_summary.py REPORT [REPORT ...] > profiles/rNN_ncu_<what>.txt
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [("dur us", "gpu__time_duration.sum"), ("dram R MB", "dram__bytes_read.sum"), ("dram W MB", "dram__bytes_write.sum"),
+        ("regs", "launch__registers_per_thread"), ("occupancy %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+        ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        ("fma pipe %", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("tensor pipe %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("smem wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+        ("smem conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+        ("warp-instr", "smsp__inst_executed.sum"), ("cycles", "sm__cycles_elapsed.max")]
+
+for rep in sys.argv[1:]:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    print(f"# {rep}")
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        u = dict(zip(hdr, units))
+        name = d.get("Kernel Name", "?")[:90]
+        print(f"## {name}  grid={d.get('Grid Size')} block={d.get('Block Size')}")
+        parts = []
+        for label, key in KEYS:
+            v = d.get(key)
+            if v in (None, ""):
+                continue
+            try:
+                f = float(v.replace(",", ""))
+                unit = u.get(key, "")
+                if label.endswith("MB") and unit == "byte":
+                    f /= 1e6
+                if label == "dur us" and unit in ("nsecond", "ns"):
+                    f /= 1e3
+                v = f"{f:.4g}" if f < 1e6 else f"{f:.3e}"
+            except ValueError:
+                pass
+            parts.append(f"{label} {v}")
+        print("   " + " | ".join(parts))
+        st = {k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): float(v)
+              for k, v in d.items() if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and v}
+        print("   stalls/issue: " + ", ".join(f"{k} {v:.2f}" for k, v in sorted(st.items(), key=lambda x: -x[1])[:7]))
