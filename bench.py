@@ -40,7 +40,7 @@ TF32_MMA_PEAK_TFLOPS = 1096.0  # measured: profiles/r01_tf32_umma_micro.txt (tcg
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of tools/opbench.py at the bench's
 # shapes (B = 24, S = 512); keyed by the label of the C-ABI call
 NCU_TRAFFIC_BYTES = {
-    "corr_bwd C32 128x128 D2=81 g2": (228.1e6 + 77.4e6, "profiles/r01_u_ncu_corr_bwd.txt"),
+    "corr_bwd C32 128x128 D2=81 g2": (228.1e6 + 75.1e6, "profiles/r02_ncu_corr_bwd_box.txt"),
     "corr_fwd C32 128x128 D9": (100.8e6 + 73.7e6, "profiles/r01_o_ncu_corr_fwd.txt"),
     "warp_bwd m2 C32 128x128 gI1=1 gI2=1": (107.0e6 + 30.9e6 + 3.2e6, "profiles/r01_t_ncu_corr_bwd_warp_bwd.txt"),
 }

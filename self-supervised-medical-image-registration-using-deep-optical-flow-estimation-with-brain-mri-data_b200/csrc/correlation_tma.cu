@@ -435,10 +435,18 @@ int launch_fwd(const float* f1, const float* f2, float* out, const CorrGeom& g, 
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-// (-DOFR_BWD_BM=4 builds the backward with 4-pixel strips = twice the warps at 96 registers: measured 171.5 us against 169.3
-// at level 2 -- the shared-memory pipe, not latency hiding, is the limit)
+// Build knobs of the backward, kept for A/B runs (tools/build_variant.py); level-2 times, DESIGN.md 4.1:
+//   OFR_BWD_BM=4    4-pixel strips = twice the warps at 96 registers: 171.5 us against 169.3 (before the two below)
+//   OFR_BWD_BOX=0   one TMA box per gradient plane (9 copy instructions per step) instead of 1-2: 169.3 us against 155.5
+//   OFR_BWD_EARLY=0 gradient stage released at the end of its step instead of once it is in registers: 155.5 against 152.8
 #ifndef OFR_BWD_BM
 #define OFR_BWD_BM 8
+#endif
+#ifndef OFR_BWD_EARLY
+#define OFR_BWD_EARLY 1
+#endif
+#ifndef OFR_BWD_BOX
+#define OFR_BWD_BOX 1
 #endif
 constexpr int kBM = OFR_BWD_BM;     // pixels per thread along x
 
@@ -462,6 +470,21 @@ struct BwdT {
     static constexpr int GS = D * GP;             // one gradient stage (D planes), floats
     static constexpr int THREADS = TH * NS * CG;
     static constexpr int FH = R2 / 2;             // the feature tile arrives as two boxes of FH rows, each with its own barrier
+    // One displacement row of the gradient in as few TMA boxes as possible (a copy instruction queues behind the CTA's
+    // shared-memory loads, so nine of them cost the issuing thread a good part of a step): the D planes of the
+    // unshifted direction are ONE box.  The shifted direction's planes are consecutive in memory in DESCENDING
+    // displacement order and may share a 16-byte aligned box origin while their column shifts differ by at most 4
+    // (the box is 4 columns wider than the tile): groups of four planes, the last group of five, each one box whose
+    // planes land in reverse order.
+    static constexpr bool GROUPED = OFR_BWD_BOX && XO == 0 && D % 4 == 1 && D >= 5;
+    __host__ __device__ static constexpr int group_lo(int tii) { return tii >= D - 5 ? D - 5 : tii & ~3; }
+    __host__ __device__ static constexpr int group_hi(int tii) { return tii >= D - 5 ? D - 1 : (tii & ~3) + 3; }
+    __host__ __device__ static constexpr int slot(int tii) {   // stage slot that holds the plane of x-displacement tii
+        return GROUPED && SHIFTED ? group_lo(tii) + (group_hi(tii) - tii) : tii;
+    }
+    __host__ __device__ static constexpr int shift(int tii) {  // columns between the box origin and the plane's first pixel
+        return GROUPED ? tii - group_lo(tii) : (tii + XO) & 3;
+    }
     static constexpr size_t SMEM = sizeof(float) * (FT + NSTG * GS) + 8 * (NSTG + 2) + 1024;
     static_assert((FT * 4) % 128 == 0 && (GP * 4) % 128 == 0 && (CB * FH * P2 * 4) % 128 == 0,
                   "TMA destinations must stay 128-byte aligned");
@@ -470,39 +493,45 @@ struct BwdT {
     static_assert(SMEM <= 227 * 1024, "tile does not fit in shared memory");
 };
 
-// one sweep over the x-displacements [T0, T0+TIC) of the staged displacement row
-template <class T, int R, int CG, int TIC, bool SHIFTED, int T0>
-__device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const float* __restrict__ fp,
-                                          float (&acc)[kBM][T::CN]) {
-    float gv[TIC][kBM];
+// registers <- the gradient values of the x-displacements [T0, T0+TIC) of the staged displacement row
+template <class T, int TIC, bool SHIFTED, int T0>
+__device__ __forceinline__ void bwd_load_g(const float* __restrict__ gp, float (&gv)[TIC][kBM]) {
     if (SHIFTED) {
-        // plane tii was staged with its box origin at x0 - R + tii rounded down to a multiple of 4: the value for target
-        // column s*8 + i sits at box column s*8 + i + ((tii + XO) & 3)
+        // plane tii was staged with its box origin shift(tii) columns left of x0 - R + tii (a multiple of 4 pixels): the
+        // value for target column s*8 + i sits at box column s*8 + i + shift(tii); aligned 128-bit loads, then select
 #pragma unroll
         for (int t = 0; t < TIC; ++t) {
-            constexpr int LEN = kBM + 4;  // aligned window that covers 8 values starting anywhere inside a float4
-            float w[LEN];
+            const int sh = T::shift(T0 + t), a0 = sh & ~3, rem = sh & 3;  // compile-time after unrolling
+            float w[kBM + 4];
 #pragma unroll
-            for (int i = 0; i < LEN; i += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + i);
-                w[i] = v.x, w[i + 1] = v.y, w[i + 2] = v.z, w[i + 3] = v.w;
+            for (int i = 0; i < kBM + 4; i += 4) {
+                if (i < kBM || rem) {
+                    const float4 v = *reinterpret_cast<const float4*>(gp + T::slot(T0 + t) * T::GP + a0 + i);
+                    w[i] = v.x, w[i + 1] = v.y, w[i + 2] = v.z, w[i + 3] = v.w;
+                }
             }
 #pragma unroll
-            for (int i = 0; i < kBM; ++i) gv[t][i] = w[i + ((T0 + t + T::XO) & 3)];
+            for (int i = 0; i < kBM; ++i) gv[t][i] = w[i + rem];
         }
     } else {
 #pragma unroll
         for (int t = 0; t < TIC; ++t)
 #pragma unroll
             for (int i = 0; i < kBM; i += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(gp + (T0 + t) * T::GP + i);
+                const float4 v = *reinterpret_cast<const float4*>(gp + T::slot(T0 + t) * T::GP + i);
                 gv[t][i] = v.x, gv[t][i + 1] = v.y, gv[t][i + 2] = v.z, gv[t][i + 3] = v.w;
             }
     }
+}
+
+// channels [K0, K1) of the thread: feature window x the gradient values in registers
+template <class T, int CG, int TIC, int T0, int K0, int K1>
+__device__ __forceinline__ void bwd_fma(const float* __restrict__ fp, const float (&gv)[TIC][kBM],
+                                        float (&acc)[kBM][T::CN]) {
     constexpr int B0 = (T0 + T::XO) & ~3;                                // aligned start of the feature window
     constexpr int BL = ((T0 + T::XO + TIC + kBM - 1) - B0 + 3) / 4 * 4;  // floats to load
 #pragma unroll
-    for (int k = 0; k < T::CN; ++k) {
+    for (int k = K0; k < K1; ++k) {
         float bv[BL];
 #pragma unroll
         for (int i = 0; i < BL; i += 4) {
@@ -516,6 +545,15 @@ __device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const fl
     }
 }
 
+// one sweep over the x-displacements [T0, T0+TIC) of the staged displacement row
+template <class T, int R, int CG, int TIC, bool SHIFTED, int T0>
+__device__ __forceinline__ void bwd_sweep(const float* __restrict__ gp, const float* __restrict__ fp,
+                                          float (&acc)[kBM][T::CN]) {
+    float gv[TIC][kBM];
+    bwd_load_g<T, TIC, SHIFTED, T0>(gp, gv);
+    bwd_fma<T, CG, TIC, T0, 0, T::CN>(fp, gv, acc);
+}
+
 template <class T, int R, int CG, int TIC, bool SHIFTED, int T0>
 struct SweepAll {
     static __device__ __forceinline__ void run(const float* gp, const float* fp, float (&acc)[kBM][T::CN]) {
@@ -526,7 +564,7 @@ struct SweepAll {
 
 template <int R, int TH, int NS, int CG, int TIC, bool SHIFTED, int NSTG, int CB>
 __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const CUtensorMap& mapG,
-                                                  float* __restrict__ gI, const CorrGeom& g, int tiles_x, int tiles_y,
+                                                  const CUtensorMap& mapGq, float* __restrict__ gI, const CorrGeom& g, int tiles_x, int tiles_y,
                                                   int cblocks, int ndir) {
     using T = BwdT<R, TH, NS, CG, TIC, SHIFTED, NSTG, CB>;
     constexpr int D = T::D;
@@ -557,10 +595,22 @@ __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const
     const int s = (tid / TH) % NS;
     const int cg = tid / (TH * NS);
 
-    // one displacement row (D planes) of the gradient into stage st, or -- prefetch -- only into the L2
+    // one displacement row (D planes) of the gradient into stage st
     auto issue_g = [&](int tji, int st) {
         float* dst = Gs + st * T::GS;
         ofr::mbar_expect_tx(&bars[st], T::GS * 4);
+        if constexpr (T::GROUPED) {
+            if constexpr (!SHIFTED) {
+                ofr::tma_load_4d(dst, &mapG, &bars[st], x0, y0, tji * D, b);  // mapG: boxes of D planes
+            } else {
+                const int pl0 = (2 * R - tji) * D + 2 * R, cy = y0 + tji - R;
+#pragma unroll 1
+                for (int lo = 0; lo < D - 5; lo += 4)  // mapGq: boxes of 4 planes; mapG: the last box, 5 planes
+                    ofr::tma_load_4d(dst + lo * T::GP, &mapGq, &bars[st], x0 - R + lo, cy, pl0 - (lo + 3), b);
+                ofr::tma_load_4d(dst + (D - 5) * T::GP, &mapG, &bars[st], x0 - R + D - 5, cy, pl0 - (D - 1), b);
+            }
+            return;
+        }
 #pragma unroll 1
         for (int tii = 0; tii < D; ++tii) {
             // SHIFTED: plane of displacement -t, rows shifted by tj here, columns shifted by ti at register fill
@@ -573,6 +623,7 @@ __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const
     if (tid == 0) {
         ofr::tma_prefetch_desc(&mapF);
         ofr::tma_prefetch_desc(&mapG);
+        ofr::tma_prefetch_desc(&mapGq);
         for (int i = 0; i < NSTG + 2; ++i) ofr::mbar_init(&bars[i], 1);
         ofr::mbar_fence_init();
     }
@@ -604,12 +655,29 @@ __device__ __forceinline__ void corr_bwd_tma_body(const CUtensorMap& mapF, const
         // feature tile layout: [half][channel][FH rows][P2] (two TMA boxes)
         const int rr = row + tji, half = rr >= T::FH ? 1 : 0;
         const float* fp = Fs + half * (CB * T::FH * T::P2) + cg * (T::FH * T::P2) + (rr - half * T::FH) * T::P2 + s * kBM;
-        SweepAll<T, R, CG, TIC, SHIFTED, 0>::run(gp, fp, acc);
-        if (tji + NSTG < D) {
-            __syncthreads();  // every thread is done reading stage st
-            if (tid == 0) {
-                ofr::fence_proxy_async();
-                issue_g(tji + NSTG, st);
+        if constexpr (OFR_BWD_EARLY && TIC == D) {
+            // the whole displacement row fits in registers: the stage is free again once every thread has loaded it
+            // (the first channel's arithmetic consumes all of it, so the loads have landed at the barrier), and its
+            // refill gets almost two steps instead of one to arrive
+            float gv[TIC][kBM];
+            bwd_load_g<T, TIC, SHIFTED, 0>(gp, gv);
+            bwd_fma<T, CG, TIC, 0, 0, 1>(fp, gv, acc);
+            if (tji + NSTG < D) {
+                __syncthreads();
+                if (tid == 0) {
+                    ofr::fence_proxy_async();
+                    issue_g(tji + NSTG, st);
+                }
+            }
+            bwd_fma<T, CG, TIC, 0, 1, T::CN>(fp, gv, acc);
+        } else {
+            SweepAll<T, R, CG, TIC, SHIFTED, 0>::run(gp, fp, acc);
+            if (tji + NSTG < D) {
+                __syncthreads();  // every thread is done reading stage st
+                if (tid == 0) {
+                    ofr::fence_proxy_async();
+                    issue_g(tji + NSTG, st);
+                }
             }
         }
     }
@@ -643,12 +711,12 @@ template <int R, int TH, int NS, int CG, int TIC, int NSTG, int CB>
 __global__ void __launch_bounds__(BwdT<R, TH, NS, CG, TIC, true, NSTG, CB>::THREADS, 1)
     corr_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapF2, const __grid_constant__ CUtensorMap mapG0,
                         const __grid_constant__ CUtensorMap mapF1, const __grid_constant__ CUtensorMap mapG1,
-                        float* __restrict__ gI1, float* __restrict__ gI2, CorrGeom g, int tiles_x, int tiles_y,
+                        const __grid_constant__ CUtensorMap mapG1q, float* __restrict__ gI1, float* __restrict__ gI2, CorrGeom g, int tiles_x, int tiles_y,
                         int cblocks, int ndir, int first) {
     if ((int)(blockIdx.x % ndir) + first == 0)
-        corr_bwd_tma_body<R, TH, NS, CG, TIC, false, NSTG, CB>(mapF2, mapG0, gI1, g, tiles_x, tiles_y, cblocks, ndir);
+        corr_bwd_tma_body<R, TH, NS, CG, TIC, false, NSTG, CB>(mapF2, mapG0, mapG0, gI1, g, tiles_x, tiles_y, cblocks, ndir);
     else
-        corr_bwd_tma_body<R, TH, NS, CG, TIC, true, NSTG, CB>(mapF1, mapG1, gI2, g, tiles_x, tiles_y, cblocks, ndir);
+        corr_bwd_tma_body<R, TH, NS, CG, TIC, true, NSTG, CB>(mapF1, mapG1, mapG1q, gI2, g, tiles_x, tiles_y, cblocks, ndir);
 }
 
 template <int R, int TH, int NS, int CG, int TIC, int NSTG, int CB>
@@ -656,11 +724,15 @@ int launch_bwd(const float* f1, const float* f2, const float* gO, float* gI1, fl
                cudaStream_t st) {
     using T0 = BwdT<R, TH, NS, CG, TIC, false, NSTG, CB>;
     using T1 = BwdT<R, TH, NS, CG, TIC, true, NSTG, CB>;
-    CUtensorMap mF2, mG0, mF1, mG1;
+    CUtensorMap mF2, mG0, mF1, mG1, mG1q;
     if (!ofr::make_tmap_nchw(&mF2, f2, g.B, g.C, g.H, g.W, T0::P2, T0::FH, CB)) return OFR_ENOTSUP;
     if (!ofr::make_tmap_nchw(&mF1, f1, g.B, g.C, g.H, g.W, T1::P2, T1::FH, CB)) return OFR_ENOTSUP;
-    if (!ofr::make_tmap_nchw(&mG0, gO, g.B, T0::D * T0::D, g.Hout, g.Wout, T0::GW, TH, 1)) return OFR_ENOTSUP;
-    if (!ofr::make_tmap_nchw(&mG1, gO, g.B, T1::D * T1::D, g.Hout, g.Wout, T1::GW, TH, 1)) return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mG0, gO, g.B, T0::D * T0::D, g.Hout, g.Wout, T0::GW, TH, T0::GROUPED ? T0::D : 1))
+        return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mG1, gO, g.B, T1::D * T1::D, g.Hout, g.Wout, T1::GW, TH, T1::GROUPED ? 5 : 1))
+        return OFR_ENOTSUP;
+    if (!ofr::make_tmap_nchw(&mG1q, gO, g.B, T1::D * T1::D, g.Hout, g.Wout, T1::GW, TH, T1::GROUPED ? 4 : 1))
+        return OFR_ENOTSUP;
     auto kern = corr_bwd_tma_kernel<R, TH, NS, CG, TIC, NSTG, CB>;
     constexpr size_t smem = T0::SMEM > T1::SMEM ? T0::SMEM : T1::SMEM;
     OFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -670,7 +742,8 @@ int launch_bwd(const float* f1, const float* f2, const float* gO, float* gI1, fl
     if (nblk >= (1ll << 30)) return OFR_ENOTSUP;
     const int ndir = (gI1 ? 1 : 0) + (gI2 ? 1 : 0);
     if (ndir == 0) return OFR_OK;
-    kern<<<(unsigned)(nblk * ndir), T0::THREADS, smem, st>>>(mF2, mG0, mF1, mG1, gI1, gI2, g, tiles_x, tiles_y, cblocks,
+    kern<<<(unsigned)(nblk * ndir), T0::THREADS, smem, st>>>(mF2, mG0, mF1, mG1, mG1q, gI1, gI2, g, tiles_x, tiles_y,
+                                                              cblocks,
                                                               ndir, gI1 ? 0 : 1);
     OFR_LAUNCH_CHECK();
     return OFR_OK;
