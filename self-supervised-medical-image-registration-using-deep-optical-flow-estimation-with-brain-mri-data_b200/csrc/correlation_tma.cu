@@ -33,6 +33,22 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef OFR_FWD_TRACE
+#define OFR_FWD_TRACE 0   // 1: clock64() timeline of CTA 0 (threads 0 and 32) per ring iteration of the forward kernel,
+#endif                    //    read back with ofr_debug_fwd_trace (tools/diag/fwd_trace.py; profiles/r02_corr_fwd_trace.txt)
+#if OFR_FWD_TRACE
+__device__ long long ofr_fwd_trace_buf[2][64][6];
+extern "C" int ofr_debug_fwd_trace(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, ofr_fwd_trace_buf, sizeof(ofr_fwd_trace_buf));
+}
+#define OFR_TR(slot)                                                                                                  \
+    do {                                                                                                              \
+        if (blockIdx.x == 0 && (tid == 0 || tid == 32) && q < 64) ofr_fwd_trace_buf[tid >> 5][q][slot] = clock64(); \
+    } while (0)
+#else
+#define OFR_TR(slot)
+#endif
+
 namespace {
 
 using ofr::CorrGeom;
@@ -165,7 +181,9 @@ __global__ void __maxnreg__(224)
     int ck = 0, tile_k = 0;
     for (int q = 0; q < total; ++q) {
         const int st = q % NST;
+        OFR_TR(0);
         ofr::mbar_wait(&bars[st], (q / NST) & 1);
+        OFR_TR(1);
         const float* ap = smem + st * T::STAGE + row * T::P1 + s * M;
         const float* bp = smem + st * T::STAGE + T::F1 + (row + tjc) * T::P2 + s * M;
 #pragma unroll 1
@@ -186,11 +204,14 @@ __global__ void __maxnreg__(224)
 #pragma unroll
                 for (int j = 0; j < D; ++j) acc[i][j] = fmaf(a[i], bv[i + j + T::XO], acc[i][j]);
         }
+        OFR_TR(2);
         __syncthreads();  // every thread is done reading stage st
+        OFR_TR(3);
         if (tid == 0 && q + NST < total) {
             ofr::fence_proxy_async();
             issue(q + NST);
         }
+        OFR_TR(4);
         if (++ck == nchunks) {
             // Tile finished.  Warp-private epilogue (no CTA barrier, so warps drift apart and overlap their phases):
             // for each x-displacement j the lanes park their M-pixel runs in the warp's staging buffer so that the NS
@@ -238,6 +259,7 @@ __global__ void __maxnreg__(224)
                 for (int j = 0; j < D; ++j) acc[i][j] = 0.f;
             ck = 0;
             ++tile_k;
+            OFR_TR(5);
         }
     }
 }
