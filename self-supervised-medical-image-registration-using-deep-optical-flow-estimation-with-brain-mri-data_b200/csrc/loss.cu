@@ -59,6 +59,7 @@ struct LossParams {
     double lamb_da, gamma, zeta;
     ScaleDev sc[OFR_LOSS_MAX_SCALES];
     int cta_begin[OFR_LOSS_MAX_SCALES + 1];  // CTA index range of each scale in the multi-scale launches
+    int grp_begin[OFR_LOSS_MAX_SCALES + 1];  // final reduction: range of thread groups that fold each scale's CTA partials
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -327,57 +328,78 @@ __global__ void __launch_bounds__(kThreads, FUSED ? 3 : 4) loss_partial_kernel(c
     }
 }
 
-// One CTA of 1024 threads: 128 threads per scale.  Thread t of a scale folds CTA partials t, t+128, ... in
-// ascending order, then a fixed-shape shuffle / shared-memory tree combines the 128 lanes: deterministic.
+#ifndef OFR_LOSS_TRACE
+#define OFR_LOSS_TRACE 0   // 1: clock64() marks of thread 0 of loss_final_kernel, read with ofr_debug_loss_trace
+#endif
+#if OFR_LOSS_TRACE
+__device__ long long ofr_loss_trace_buf[8];
+#define OFR_LT(i) do { if (threadIdx.x == 0) ofr_loss_trace_buf[i] = clock64(); } while (0)
+#else
+#define OFR_LT(i)
+#endif
+
+// One CTA.  The CTA partials of a scale are a dense [partial][kNumPart] array of doubles; the kFinalGroups groups of
+// kNumPart threads are dealt to the scales in proportion to their partial counts (fill_params).  Group j of a scale's G
+// folds partials j, j+G, ... in ascending order, lane k of the group owning component k: consecutive threads read
+// consecutive doubles (the first version read them at an 88-byte stride with 11 accumulators per thread in 64 registers
+// and spent 26 000 of the kernel's 31 000 cycles here).  One thread per (scale, component) then adds the group results
+// in group order.  Everything is a fixed function of the launch shape: deterministic.
+constexpr int kFinalGroups = 1024 / kNumPart;          // 93
+constexpr int kFinalBatch = 8;                         // loads in flight per thread (12, 16, 24: no faster)
+__device__ __forceinline__ double part_identity(int k) {
+    return (k == P_MINW || k == P_MINF) ? 1e300 : (k == P_MAXW || k == P_MAXF) ? -1e300 : 0.0;
+}
+// the component index is a run-time value here: all three candidates are formed and one is selected, so that the
+// compiler emits selects (a `k == ...` chain became an indirect branch through a jump table per element: 480 cycles each)
+struct PartOp {
+    bool is_min, is_max;
+    __device__ explicit PartOp(int k) : is_min(k == P_MINW || k == P_MINF), is_max(k == P_MAXW || k == P_MAXF) {}
+    __device__ __forceinline__ double operator()(double a, double b) const {
+        const double sum = a + b, lo = fmin(a, b), hi = fmax(a, b);
+        return is_min ? lo : is_max ? hi : sum;
+    }
+};
 __global__ void __launch_bounds__(1024) loss_final_kernel(const __grid_constant__ LossParams p,
                                                           const double* __restrict__ partials,
                                                           double* __restrict__ state, double* __restrict__ out4) {
-    __shared__ double red[OFR_LOSS_MAX_SCALES][4][kNumPart];
-    const int s = threadIdx.x >> 7, t = threadIdx.x & 127, wq = t >> 5;
-    double v[kNumPart];
+    __shared__ double red[kFinalGroups][kNumPart];
+    OFR_LT(0);
+    {
+        const int g = threadIdx.x / kNumPart, k = threadIdx.x - g * kNumPart;
+        if (g < p.grp_begin[p.n]) {
+            int s = 0;  // scale of the group: grp_begin ascends (fixed offsets into the parameters: no dependent look-ups)
 #pragma unroll
-    for (int k = 0; k < kNumPart; ++k) v[k] = (k == P_MINW || k == P_MINF) ? 1e300 : (k == P_MAXW || k == P_MAXF) ? -1e300 : 0.0;
-    if (s < p.n) {
-        // four CTA partials per step, all their loads issued before the (ordered) adds: the loop is latency bound
-        const int cend = p.cta_begin[s + 1];
-        for (int c = p.cta_begin[s] + t; c < cend; c += 4 * 128) {
-            double x[4][kNumPart];
+            for (int i = 1; i < OFR_LOSS_MAX_SCALES; ++i) s += (i < p.n && g >= p.grp_begin[i]) ? 1 : 0;
+            const int G = p.grp_begin[s + 1] - p.grp_begin[s], cend = p.cta_begin[s + 1];
+            const PartOp fold(k);
+            const double ident = part_identity(k);
+            double v = ident;
+            for (int c = p.cta_begin[s] + (g - p.grp_begin[s]); c < cend; c += kFinalBatch * G) {
+                double x[kFinalBatch];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < kFinalBatch; ++q)
+                    x[q] = (c + q * G < cend) ? partials[(long long)(c + q * G) * kNumPart + k] : ident;
 #pragma unroll
-                for (int k = 0; k < kNumPart; ++k)
-                    x[q][k] = (c + q * 128 < cend) ? partials[(long long)(c + q * 128) * kNumPart + k]
-                                                   : ((k == P_MINW || k == P_MINF) ? 1e300 : (k == P_MAXW || k == P_MAXF) ? -1e300 : 0.0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int k = 0; k < kNumPart; ++k)
-                    v[k] = (k == P_MINW || k == P_MINF) ? fmin(v[k], x[q][k])
-                           : (k == P_MAXW || k == P_MAXF) ? fmax(v[k], x[q][k]) : v[k] + x[q][k];
+                for (int q = 0; q < kFinalBatch; ++q) v = fold(v, x[q]);
+            }
+            red[g][k] = v;
         }
     }
-#pragma unroll
-    for (int k = 0; k < kNumPart; ++k) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const double x = __shfl_xor_sync(0xffffffffu, v[k], d);
-            v[k] = (k == P_MINW || k == P_MINF) ? fmin(v[k], x) : (k == P_MAXW || k == P_MAXF) ? fmax(v[k], x) : v[k] + x;
-        }
-        if ((t & 31) == 0) red[s][wq][k] = v[k];
-    }
+    OFR_LT(1);
     __syncthreads();
+    OFR_LT(2);
+    const int s = threadIdx.x >> 7, t = threadIdx.x & 127;  // from here on: 128 threads per scale
     if (s < p.n && t < kNumPart) {
         const int k = t;
-        double x = red[s][0][k];
-        for (int q = 1; q < 4; ++q) {
-            const double y = red[s][q][k];
-            x = (k == P_MINW || k == P_MINF) ? fmin(x, y) : (k == P_MAXW || k == P_MAXF) ? fmax(x, y) : x + y;
-        }
+        const PartOp fold(k);
+        double x = red[p.grp_begin[s]][k];  // (four interleaved chains were not faster than this one: 5 000 against 3 900 cycles)
+        for (int g = p.grp_begin[s] + 1; g < p.grp_begin[s + 1]; ++g) x = fold(x, red[g][k]);
         state[s * OFR_LOSS_STATE_DOUBLES + k] = x;
     }
     __syncthreads();
     // per-scale terms: one thread per scale (float64 sqrt / divisions are long serial chains), then thread 0 adds them
     __shared__ double terms[OFR_LOSS_MAX_SCALES][3];
+    OFR_LT(3);
     if (s < p.n && t == 0) {
         const int i = s;
         double* st = state + i * OFR_LOSS_STATE_DOUBLES;
@@ -398,7 +420,9 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(const __grid_constant_
         terms[i][1] = wi * ncc;
         terms[i][2] = wi * smooth;
     }
+    OFR_LT(4);
     __syncthreads();
+    OFR_LT(5);
     if (threadIdx.x != 0) return;
     double tp = 0.0, tc = 0.0, ts = 0.0;
     for (int i = 0; i < p.n; ++i) {  // ascending, like the reference's loop (loss.py:74-80)
@@ -412,6 +436,7 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(const __grid_constant_
     out4[1] = C;
     out4[2] = S;
     out4[3] = P + S + C;  // loss.py:83 adds in this order
+    OFR_LT(6);
 }
 
 template <int VEC>
@@ -689,12 +714,33 @@ int fill_params(LossParams& p, const float* fixed, int B, int Hs, int Ws, const 
     }
     p.cta_begin[OFR_LOSS_MAX_SCALES] = at;
     for (int i = n; i <= OFR_LOSS_MAX_SCALES; ++i) p.cta_begin[i] = at;
+    // final reduction: the thread groups are dealt to the scales in proportion to their CTA partials, at least one each
+    int groups[OFR_LOSS_MAX_SCALES], sum = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long share = (long long)kFinalGroups * (p.cta_begin[i + 1] - p.cta_begin[i]) / (at > 0 ? at : 1);
+        groups[i] = share < 1 ? 1 : (int)share;
+        sum += groups[i];
+    }
+    while (sum > kFinalGroups) {  // the floors were lifted to 1 for small scales: take the excess from the largest share
+        int big = 0;
+        for (int i = 1; i < n; ++i)
+            if (groups[i] > groups[big]) big = i;
+        --groups[big], --sum;
+    }
+    p.grp_begin[0] = 0;
+    for (int i = 0; i < OFR_LOSS_MAX_SCALES; ++i) p.grp_begin[i + 1] = p.grp_begin[i] + (i < n ? groups[i] : 0);
     return OFR_OK;
 }
 
 size_t ws_bytes_for(int total_ctas) { return ofr::align_up(sizeof(double) * kNumPart * (size_t)total_ctas, 256); }
 
 }  // namespace
+
+#if OFR_LOSS_TRACE
+extern "C" int ofr_debug_loss_trace(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, ofr_loss_trace_buf, sizeof(ofr_loss_trace_buf));
+}
+#endif
 
 extern "C" size_t ofr_loss_workspace(int n_scales) {
     if (n_scales < 1 || n_scales > OFR_LOSS_MAX_SCALES) return 0;
