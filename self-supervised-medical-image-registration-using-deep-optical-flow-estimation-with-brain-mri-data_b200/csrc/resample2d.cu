@@ -423,6 +423,19 @@ __global__ void __launch_bounds__(kTileThreads) resample_prep_kernel(const float
 // HW != 0: the plane size Hf*Wf == Hin*Win is this compile-time constant, so the channel offsets of the 16-channel
 // gathers are instruction immediates (with a run-time stride a third of the kernel's issue slots were 64-bit address
 // arithmetic).  Instantiated for the power-of-two maps of the PWC-Net pyramid.
+#ifndef OFR_WARP_TRACE
+#define OFR_WARP_TRACE 0   // 1: clock64() marks of thread 0 of one CTA of resample_bwd_fused_kernel, read back with
+#endif                     //    ofr_debug_warp_trace (tools/diag/warp_bwd_trace.py; profiles/r02_warp_bwd_study.txt)
+#if OFR_WARP_TRACE
+__device__ long long ofr_warp_trace_buf[16];
+#define OFR_WT(i)                                                                                                  \
+    do {                                                                                                           \
+        if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 7 && blockIdx.z == 5) ofr_warp_trace_buf[i] = clock64(); \
+    } while (0)
+#else
+#define OFR_WT(i)
+#endif
+
 template <int MODE, bool WANT1, bool WANT2, int HW>
 __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
     const float* __restrict__ in1, const float* __restrict__ gO, const int4* __restrict__ recs,
@@ -530,6 +543,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                 }
         }
     };
+    OFR_WT(0);
     prefetch_chunk(cbeg);
 
     int total = 0;
@@ -543,6 +557,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
             const int bin = bin_of(r);
             if (bin >= 0) atomicAdd(&ccount[bin], 1);
         });
+        OFR_WT(1);
         // exclusive scan of the kCells counts (two cells per thread)
         {
             const int i0 = 2 * tid, i1 = 2 * tid + 1;
@@ -573,6 +588,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
             __syncthreads();
         }
     }
+    OFR_WT(2);
     const bool staged = WANT1 && total <= kRecCap;
     int tot_e = 0, s1 = 0, s2 = 0, s3 = 0;
     if (staged) {
@@ -580,6 +596,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
             const int bin = bin_of(r);
             if (bin >= 0) srec[coff[bin] + atomicAdd(&ccount[bin], 1)] = r;
         });
+        OFR_WT(3);
         // canonical order inside every cell: ascending source offset (one thread per cell, insertion sort in shared memory)
         for (int cell = tid; cell < kCells; cell += kTileThreads) {
             const int o = coff[cell], n = coff[cell + 1] - o;
@@ -609,6 +626,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
         src = r.x;
         w = weight_of(r);
     };
+    OFR_WT(4);
     if (staged) {  // decode the first kListCap records once; the channel sweeps then only gather + FMA
         const int nlist = min(tot_e, kListCap);
         for (int e = 0; e < nlist; ++e) {
@@ -634,6 +652,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
         }
     }
     float ax = 0.f, ay = 0.f;
+    OFR_WT(5);
+    int wt = 6;  // trace slot of the next mark (unused without OFR_WARP_TRACE)
+    (void)wt;
 
     for (int c0 = cbeg; c0 < cend; c0 += kChunk) {
         const int nc = min(kChunk, g.C - c0);
@@ -692,6 +713,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                     if (k < nc) o[k * hwi] = acc[k];
             }
         }
+        OFR_WT(wt), ++wt;
         if (WANT2 && live) {
             // four tap pointers and the own-pixel pointer, bumped plane by plane (invalid taps never dereferenced)
             const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
@@ -707,6 +729,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                 ay = fmaf(gv, fmaf(owx1, br - tr, owx0 * (bl - tl)), ay);
             }
         }
+        OFR_WT(wt), ++wt;
     }
     if (WANT2) {
         if (csplit == 1) {
@@ -983,3 +1006,9 @@ extern "C" int ofr_stn_multi_fwd(const ofr_stn_scale_t* scales, int n_scales, in
 extern "C" int ofr_stn_multi_bwd(const ofr_stn_scale_t* scales, int n_scales, int B, int C, ofr_stream_t stream) {
     return stn_multi(scales, n_scales, B, C, true, (cudaStream_t)stream);
 }
+
+#if OFR_WARP_TRACE
+extern "C" int ofr_debug_warp_trace(long long* host) {
+    return (int)cudaMemcpyFromSymbol(host, ofr_warp_trace_buf, sizeof(ofr_warp_trace_buf));
+}
+#endif
