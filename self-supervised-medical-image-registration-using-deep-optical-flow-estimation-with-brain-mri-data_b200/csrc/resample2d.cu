@@ -713,7 +713,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                     if (k < nc) o[k * hwi] = acc[k];
             }
         }
-        OFR_WT(wt), ++wt;
+        OFR_WT(wt);
+        ++wt;
         if (WANT2 && live) {
             // four tap pointers and the own-pixel pointer, bumped plane by plane (invalid taps never dereferenced)
             const float* img = in1 + ((size_t)b * g.C + c0) * hwi;
@@ -729,7 +730,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) resample_bwd_fused_kernel(
                 ay = fmaf(gv, fmaf(owx1, br - tr, owx0 * (bl - tl)), ay);
             }
         }
-        OFR_WT(wt), ++wt;
+        OFR_WT(wt);
+        ++wt;
     }
     if (WANT2) {
         if (csplit == 1) {
