@@ -218,7 +218,19 @@ def run_ours(args):
     if world > 1:
         if use_graph:  # whole-step capture with DDP (PyTorch CUDA-graphs note): no async NCCL error handling
             os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner (and, with NCCL_DEBUG set, its log) on stdout while the communicator is built:
+        # point fd 1 at stderr for that moment, so that stdout carries the ONE JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()  # first collective: the communicator exists after it
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from ofr_b200.harness import synthetic_pairs, make_optimizer, train_step, GraphedStep
     from ofr_b200.profiling import KernelTimer, ClockSampler
 
