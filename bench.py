@@ -59,11 +59,13 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ model builders
-def build_gpu_step(device, channels_last=False, fused_loss=True):
+def build_gpu_step(device, channels_last=False, fused_loss=True, flow_heads=True):
     import ofr_b200 as ofr
     from ofr_b200.harness import PWCNetHost, RegistrationStep
     torch.manual_seed(6)
-    host = PWCNetHost(md=4).to(device)
+    # flow_heads: predict_flow* / dc_conv7 / deconv* / upfeat* (two output channels) on ofr_flowconv3 / ofr_flowdeconv4
+    # instead of cuDNN; same parameters
+    host = PWCNetHost(md=4, fast_heads=flow_heads).to(device)
     if channels_last:  # host-model memory format only; the ofr_b200 layers take / return NCHW (they call .contiguous())
         host = host.to(memory_format=torch.channels_last)
     host.deconv0.requires_grad_(False)  # unused in the forward (PWCNet.py:126,274): keep it out of DDP's reducer
@@ -241,7 +243,8 @@ def run_ours(args):
         B = args.batch
     S = args.size
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
-    step, ofr = build_gpu_step(device, channels_last=args.channels_last, fused_loss=bool(args.fused_loss))
+    step, ofr = build_gpu_step(device, channels_last=args.channels_last, fused_loss=bool(args.fused_loss),
+                               flow_heads=bool(args.flow_heads))
     if world > 1:
         ddp_kw = dict(device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_cap_mb,
                       static_graph=True)
@@ -405,6 +408,7 @@ def run_ours(args):
                        "host_memory_format": "channels_last" if args.channels_last else "contiguous (NCHW)",
                        "cudnn_benchmark": bool(args.cudnn_benchmark), "ddp_bucket_cap_mb": args.bucket_cap_mb if world > 1 else None,
                        "loss": "fused stn + OFEloss (ofr_regloss_fwd/bwd)" if args.fused_loss else "stn_multi then OFEloss",
+                       "flow_heads": "ofr_flowconv3 / ofr_flowdeconv4 (fp32)" if args.flow_heads else "cuDNN",
                        "l2": "working set (activations > 1 GB per step) exceeds the 126 MB L2; no explicit flush"},
             "step_modes": {"eager_ms_per_step": eager_ms, "cuda_graph_ms_per_step": graph_ms, "cuda_graph_error": graph_err,
                            "headline": "cuda_graph" if headline_graph else "eager",
@@ -445,6 +449,8 @@ def main():
     ap.add_argument("--channels-last", type=int, default=0, help="host model (cuDNN convolutions) in channels_last")
     ap.add_argument("--fused-loss", type=int, default=1,
                     help="1: stn warps + OFEloss as the fused registration_loss; 0: stn_warp_multi then OFEloss")
+    ap.add_argument("--flow-heads", type=int, default=1,
+                    help="1: the decoder's two-output-channel layers on the flow-head kernels (SURVEY 8f-4); 0: cuDNN")
     ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the host model")
     ap.add_argument("--cuda-graph", type=int, default=1, help="also time the step as one captured CUDA graph")
     ap.add_argument("--bucket-cap-mb", type=float, default=8.0,

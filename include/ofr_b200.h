@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define OFR_ABI_VERSION 2
+#define OFR_ABI_VERSION 3
 
 typedef void* ofr_stream_t; /* cudaStream_t */
 
@@ -232,6 +232,26 @@ int ofr_regloss_bwd(const float* fixed, int B, int Hs, int Ws,
                     const ofr_regloss_scale_t* scales, int n_scales,
                     double lamb_da, double gamma, double zeta,
                     const double* grad4, const double* state, ofr_stream_t stream);
+
+/* ------------------------------------------------------------------ Flow heads of the decoder
+ * Replace the cuDNN calls behind the two-output-channel layers of PWC/models/PWCNet.py:
+ *   predict_flow(in_planes) = nn.Conv2d(in_planes, 2, kernel_size=3, stride=1, padding=1)          -- :30-31, 81..121, 134
+ *   deconv(in_planes, 2)    = nn.ConvTranspose2d(in_planes, 2, kernel_size=4, stride=2, padding=1) -- :33-34, 82..124
+ * Weights in PyTorch's layouts: Conv2d [2][C][3][3], ConvTranspose2d [C][2][4][4]; bias [2] or NULL.  fp32 arithmetic.
+ * W % 4 == 0 and 16-byte aligned x / out / gO / gX, else OFR_ENOTSUP (the caller keeps its own convolution).
+ *   flowconv3:   x [B,C,H,W] -> out [B,2,H,W]          flowdeconv4: x [B,C,H,W] -> out [B,2,2H,2W]
+ * Backward: gX (gradient of x), gW + gB (gradients of weight and bias; gB may be NULL) -- gX or gW may be NULL.
+ * Workspace: `*_workspace(..., backward)` bytes, 256-byte aligned (0 = none needed).  Deterministic (no atomics). */
+size_t ofr_flowconv3_workspace(int B, int C, int H, int W, int backward);
+int ofr_flowconv3_fwd(const float* x, const float* w, const float* bias, float* out, int B, int C, int H, int W,
+                      void* ws, size_t ws_bytes, ofr_stream_t stream);
+int ofr_flowconv3_bwd(const float* x, const float* w, const float* gO, float* gX, float* gW, float* gB,
+                      int B, int C, int H, int W, void* ws, size_t ws_bytes, ofr_stream_t stream);
+size_t ofr_flowdeconv4_workspace(int B, int C, int H, int W, int backward);
+int ofr_flowdeconv4_fwd(const float* x, const float* w, const float* bias, float* out, int B, int C, int H, int W,
+                        void* ws, size_t ws_bytes, ofr_stream_t stream);
+int ofr_flowdeconv4_bwd(const float* x, const float* w, const float* gO, float* gX, float* gW, float* gB,
+                        int B, int C, int H, int W, void* ws, size_t ws_bytes, ofr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,11 +14,12 @@ from .layers import (Correlation, Resample2d, ChannelNorm, stn_warp, stn_warp_mu
 from .loss import OFEloss, registration_loss, photometric_loss, correlation_loss, smoothness_loss
 from .registration import OpticalFlowReg, grid_generator, round_clamp_labels
 from .pairs import ElasticPairGenerator, control_grid_size
+from .flowhead import FlowConv2d, FlowUpsample2d, accelerate_flow_heads
 from .shims import install as install_shims, uninstall as uninstall_shims
 
 __all__ = [
     "Correlation", "Resample2d", "ChannelNorm", "stn_warp", "stn_warp_multi", "pwc_warp", "channelnorm_diff", "spatial_correlation_sample",
     "correlation_out_shape", "OFEloss", "registration_loss", "photometric_loss", "correlation_loss", "smoothness_loss",
-    "OpticalFlowReg", "grid_generator", "round_clamp_labels", "ElasticPairGenerator", "control_grid_size",
+    "OpticalFlowReg", "grid_generator", "round_clamp_labels", "ElasticPairGenerator", "control_grid_size", "FlowConv2d", "FlowUpsample2d", "accelerate_flow_heads",
     "install_shims", "uninstall_shims", "build", "launch_count", "LIB_PATH", "EXPORTS",
 ]

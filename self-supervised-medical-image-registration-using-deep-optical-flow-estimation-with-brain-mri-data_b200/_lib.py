@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 # OFR_B200_LIB: development switch of the PYTHON loader (A/B runs of kernel variants built by tools/build_variant.py);
 # the library itself reads no environment variable
 LIB_PATH = os.environ.get("OFR_B200_LIB") or os.path.join(PKG_DIR, "libofr_b200.so")
-SOURCES = ["abi.cu", "channelnorm.cu", "resample2d.cu", "correlation.cu", "correlation_tma.cu", "correlation_umma.cu", "loss.cu"]
+SOURCES = ["abi.cu", "channelnorm.cu", "resample2d.cu", "correlation.cu", "correlation_tma.cu", "correlation_umma.cu", "loss.cu", "flowhead.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -134,6 +134,12 @@ def _declare(lib):
                                     vp, vp, vp, c_size_t, vp]),
         "ofr_regloss_bwd": (c_int, [vp, c_int, c_int, c_int, ctypes.POINTER(RegLossScale), c_int, dbl, dbl, dbl,
                                     vp, vp, vp]),
+        "ofr_flowconv3_workspace": (c_size_t, [c_int] * 5),
+        "ofr_flowconv3_fwd": (c_int, [vp, vp, vp, vp] + [c_int] * 4 + [vp, c_size_t, vp]),
+        "ofr_flowconv3_bwd": (c_int, [vp, vp, vp, vp, vp, vp] + [c_int] * 4 + [vp, c_size_t, vp]),
+        "ofr_flowdeconv4_workspace": (c_size_t, [c_int] * 5),
+        "ofr_flowdeconv4_fwd": (c_int, [vp, vp, vp, vp] + [c_int] * 4 + [vp, c_size_t, vp]),
+        "ofr_flowdeconv4_bwd": (c_int, [vp, vp, vp, vp, vp, vp] + [c_int] * 4 + [vp, c_size_t, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == the library does not export a declared symbol
@@ -147,7 +153,8 @@ EXPORTS = ["ofr_abi_version", "ofr_error_string", "ofr_launch_count", "ofr_corr_
            "ofr_corr_bwd", "ofr_resample_fwd", "ofr_resample_fwd_scaled", "ofr_resample_bwd_workspace", "ofr_resample_bwd",
            "ofr_resample_bwd_scaled", "ofr_stn_multi_fwd", "ofr_stn_multi_bwd",
            "ofr_chnorm_fwd", "ofr_chnorm_bwd", "ofr_chnorm_diff_fwd", "ofr_chnorm_diff_bwd", "ofr_loss_workspace", "ofr_loss_fwd", "ofr_loss_bwd",
-           "ofr_regloss_fwd", "ofr_regloss_bwd"]
+           "ofr_regloss_fwd", "ofr_regloss_bwd", "ofr_flowconv3_workspace", "ofr_flowconv3_fwd", "ofr_flowconv3_bwd",
+           "ofr_flowdeconv4_workspace", "ofr_flowdeconv4_fwd", "ofr_flowdeconv4_bwd"]
 
 
 def lib():

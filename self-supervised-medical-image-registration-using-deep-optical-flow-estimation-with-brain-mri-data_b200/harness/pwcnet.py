@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..layers import Correlation, pwc_warp
+from ..flowhead import accelerate_flow_heads
 
 # (level, feature channels) from fine to coarse: pyramid levels 1..6
 _PYRAMID = [(1, 16), (2, 32), (3, 64), (4, 96), (5, 128), (6, 196)]
@@ -26,7 +27,7 @@ def _conv(cin, cout, stride=1, dilation=1):
 
 
 class PWCNetHost(nn.Module):
-    def __init__(self, md=4, corr=None, warp=None):
+    def __init__(self, md=4, corr=None, warp=None, fast_heads=None):
         super().__init__()
         self.md = md
         cin = 1
@@ -70,6 +71,10 @@ class PWCNetHost(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_in")
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
+        # product path: the two-output-channel layers (predict_flow*, dc_conv7, deconv*, upfeat*) on the flow-head kernels
+        # (SURVEY 8f-4); same parameters and state dict.  Off with injected layers (the CPU oracle has no CUDA tensors).
+        if self._fused if fast_heads is None else fast_heads:
+            accelerate_flow_heads(self)
 
     def _features(self, im):
         feats, x = {}, im

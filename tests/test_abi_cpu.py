@@ -29,7 +29,7 @@ def test_header_symbols_all_exported(built):
 
 def test_abi_version_and_error_strings(built):
     lib = built._lib.lib()
-    assert lib.ofr_abi_version() == 2
+    assert lib.ofr_abi_version() == 3
     assert lib.ofr_error_string(0) == b"ok"
     for code in (1, 2, 3):
         assert len(lib.ofr_error_string(code)) > 5
