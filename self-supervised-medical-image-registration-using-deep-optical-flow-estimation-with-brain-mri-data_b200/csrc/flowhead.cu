@@ -219,10 +219,28 @@ __device__ __forceinline__ void warp_sum(float (&v)[N]) {
         for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
 }
 
-// partial[split][c][o*9 + k] = sum over the split's patches of gO[o][p] * x[c][p + k - 1].  A WARP owns a channel pair and
-// its lanes walk the split's patches; the four warps of a CTA own four pairs and walk the SAME patches, so the gradient
-// values they all need come out of the L1 after the first warp has fetched them.  Pair 0 also sums gO itself (bias
-// gradient) into pbias[split][2].
+// one row of the 4 x 6 neighbourhood: 4 pixels at x0 plus the columns beside them (zero outside the map)
+__device__ __forceinline__ void load_row6(const float* __restrict__ plane, int y, int x0, int H, int W, bool lv, bool cv, float (&v)[6]) {
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f, r = 0.f;
+    if ((unsigned)y < (unsigned)H) {
+        const float* row = plane + (long long)y * W + x0;
+        c = ofr::ldg4(row);
+        if (lv) l = __ldg(row - 1);
+        if (cv) r = __ldg(row + 4);
+    }
+    v[0] = l, v[1] = c.x, v[2] = c.y, v[3] = c.z, v[4] = c.w, v[5] = r;
+}
+
+// row pairs a lane walks down in the 3x3 weight-gradient kernel: a quarter of the map's, between 2 and 16
+__host__ __device__ inline int walk_rows(int rp) { return rp >= 64 ? 16 : rp >= 8 ? rp / 4 : rp >= 2 ? 2 : 1; }
+
+// partial[split][c][o*9 + k] = sum over the split's patches of gO[o][p] * x[c][p + k - 1].  A WARP owns a channel pair;
+// its lanes own 32 neighbouring 4-pixel columns and walk walk_rows() row pairs DOWN them, so of the four rows a patch needs
+// two are still in registers from the patch above (x is read once, 16 instead of 28 loads per 288 FMAs), and the rows
+// of the next patch are loaded before the arithmetic of this one.  The four warps of a CTA own four pairs and walk the
+// SAME columns: the gradient rows they all need come out of the L1 after the first warp has fetched them.  Pair 0 also
+// sums gO itself (bias gradient) into pbias[split][2].
 __global__ void __launch_bounds__(kThreads) conv3_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gO,
                                                                float* __restrict__ partial, float* __restrict__ pbias,
                                                                Geo g, int splits) {
@@ -231,45 +249,88 @@ __global__ void __launch_bounds__(kThreads) conv3_bwd_w_kernel(const float* __re
     if (c0 >= g.C) return;  // whole warp
     const bool two = c0 + 1 < g.C;
     const long long hw = (long long)g.H * g.W;
+    const int wrows = walk_rows(g.rp), nrb = (g.rp + wrows - 1) / wrows;
+    const long long ncols = (long long)g.B * nrb * g.gx;
     float acc[38];  // [ch][o][ky][kx] (36) + the two bias sums
 #pragma unroll
     for (int k = 0; k < 38; ++k) acc[k] = 0.f;
-    for (long long item = (long long)blockIdx.y * 32 + lane; item < g.items; item += (long long)splits * 32) {
-        const Patch p = patch_of(g, item);
-        float gv[2][2][4];
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.y0 + r < g.H) t = ofr::ldg4(gO + ((long long)p.b * 2 + o) * hw + (long long)(p.y0 + r) * g.W + p.x0);
-                gv[o][r][0] = t.x, gv[o][r][1] = t.y, gv[o][r][2] = t.z, gv[o][r][3] = t.w;
-            }
-        float v[2][4][6];
-        load_patch(x + ((long long)p.b * g.C + c0) * hw, g, p, v[0]);
-        if (two) load_patch(x + ((long long)p.b * g.C + c0 + 1) * hw, g, p, v[1]);
-        if (pair == 0) {
+    for (long long col = (long long)blockIdx.y * 32 + lane; col < ncols; col += (long long)splits * 32) {
+        const int gi = (int)(col % g.gx);
+        const long long t = col / g.gx;
+        const int rb = (int)(t % nrb), b = (int)(t / nrb);
+        const int r0 = rb * wrows, r1 = min(g.rp, r0 + wrows), x0 = 4 * gi;
+        const bool lv = x0 > 0, cv = x0 + 4 < g.W;
+        const float* xa = x + ((long long)b * g.C + c0) * hw;
+        const float* xb = two ? xa + hw : xa;
+        const float* ga = gO + (long long)b * 2 * hw;
+        float v[2][4][6], gv[2][2][4];
+        auto load_g = [&](int y0, float (&d)[2][2][4]) {
 #pragma unroll
             for (int o = 0; o < 2; ++o)
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
+                for (int r = 0; r < 2; ++r) {
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (y0 + r < g.H) q = ofr::ldg4(ga + o * hw + (long long)(y0 + r) * g.W + x0);
+                    d[o][r][0] = q.x, d[o][r][1] = q.y, d[o][r][2] = q.z, d[o][r][3] = q.w;
+                }
+        };
+        // rows 2*r0 - 1 .. 2*r0 + 2 of both channels and the first gradient rows
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[36 + o] += gv[o][r][i];
+        for (int i = 0; i < 4; ++i) {
+            load_row6(xa, 2 * r0 - 1 + i, x0, g.H, g.W, lv, cv, v[0][i]);
+            load_row6(xb, 2 * r0 - 1 + i, x0, g.H, g.W, lv, cv, v[1][i]);
         }
+        load_g(2 * r0, gv);
+        for (int r = r0; r < r1; ++r) {
+            // the next patch's two new rows and gradient rows, in flight during this patch's arithmetic
+            float nv[2][2][6], ng[2][2][4];
+            const bool more = r + 1 < r1;
+            if (more) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            if (ch == 1 && !two) break;
+                for (int i = 0; i < 2; ++i) {
+                    load_row6(xa, 2 * r + 3 + i, x0, g.H, g.W, lv, cv, nv[0][i]);
+                    load_row6(xb, 2 * r + 3 + i, x0, g.H, g.W, lv, cv, nv[1][i]);
+                }
+                load_g(2 * r + 2, ng);
+            }
+            if (pair == 0) {
 #pragma unroll
-            for (int o = 0; o < 2; ++o)
+                for (int o = 0; o < 2; ++o)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+                    for (int q = 0; q < 2; ++q)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
+                        for (int i = 0; i < 4; ++i) acc[36 + o] += gv[o][q][i];
+            }
 #pragma unroll
-                        for (int r = 0; r < 2; ++r)
+            for (int ch = 0; ch < 2; ++ch) {
+                if (ch == 1 && !two) break;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                acc[ch * 18 + o * 9 + ky * 3 + kx] = fmaf(gv[o][r][i], v[ch][r + ky][i + kx], acc[ch * 18 + o * 9 + ky * 3 + kx]);
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    acc[ch * 18 + o * 9 + ky * 3 + kx] = fmaf(gv[o][q][i], v[ch][q + ky][i + kx], acc[ch * 18 + o * 9 + ky * 3 + kx]);
+            }
+            if (more) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        v[ch][0][j] = v[ch][2][j], v[ch][1][j] = v[ch][3][j];
+                        v[ch][2][j] = nv[ch][0][j], v[ch][3][j] = nv[ch][1][j];
+                    }
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) gv[o][q][i] = ng[o][q][i];
+            }
         }
     }
     warp_sum<38>(acc);
@@ -459,47 +520,84 @@ __global__ void __launch_bounds__(kThreads) deconv4_bwd_x_kernel(const float* __
     }
 }
 
+// one row of the 4 x 10 output-gradient neighbourhood of a row patch (zero outside the 2H x 2W map)
+__device__ __forceinline__ void load_grow10(const float* __restrict__ plane, int Y, int X0, int H2, int W2, float (&v)[10]) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    float l = 0.f, r = 0.f;
+    if ((unsigned)Y < (unsigned)H2) {
+        const float* row = plane + (long long)Y * W2 + X0;
+        a = ofr::ldg4(row), c = ofr::ldg4(row + 4);
+        if (X0 > 0) l = __ldg(row - 1);
+        if (X0 + 8 < W2) r = __ldg(row + 8);
+    }
+    v[0] = l, v[1] = a.x, v[2] = a.y, v[3] = a.z, v[4] = a.w, v[5] = c.x, v[6] = c.y, v[7] = c.z, v[8] = c.w, v[9] = r;
+}
+
 // partial[split][c][o*16 + k] = sum over the split's row patches of x[c][y][x] * gO[o][2y - 1 + ky][2x - 1 + kx]; warps and
-// lanes as in conv3_bwd_w_kernel
+// lanes as in conv3_bwd_w_kernel: a lane walks walk_rows(H) input rows down its 4-pixel column, and of the four gradient
+// rows 2y-1 .. 2y+2 it needs two are still in registers from the row above
 __global__ void __launch_bounds__(kThreads) deconv4_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gO,
                                                                  float* __restrict__ partial, float* __restrict__ pbias,
-                                                                 Geo g, long long items, int splits) {
+                                                                 Geo g, int splits) {
     const int lane = threadIdx.x & 31, pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int c0 = pair * 2;
     if (c0 >= g.C) return;  // whole warp
     const bool two = c0 + 1 < g.C;
     const long long hw = (long long)g.H * g.W;
+    const int H2 = 2 * g.H, W2 = 2 * g.W;
+    const int wrows = walk_rows(g.H), nrb = (g.H + wrows - 1) / wrows;
+    const long long ncols = (long long)g.B * nrb * g.gx;
     float acc[66];  // [ch][o][ky][kx] (64) + the two bias sums
 #pragma unroll
     for (int k = 0; k < 66; ++k) acc[k] = 0.f;
-    for (long long item = (long long)blockIdx.y * 32 + lane; item < items; item += (long long)splits * 32) {
-        const RowPatch p = rowpatch_of(g, item);
+    for (long long col = (long long)blockIdx.y * 32 + lane; col < ncols; col += (long long)splits * 32) {
+        const int gi = (int)(col % g.gx);
+        const long long t = col / g.gx;
+        const int rb = (int)(t % nrb), b = (int)(t / nrb);
+        const int y0 = rb * wrows, y1 = min(g.H, y0 + wrows), x0 = 4 * gi, X0 = 2 * x0;
+        const float* xa = x + ((long long)b * g.C + c0) * hw + x0;
+        const float* g0 = gO + (long long)b * 2 * 4 * hw;
+        const float* g1 = g0 + 4 * hw;
         float gv[2][4][10];
 #pragma unroll
-        for (int o = 0; o < 2; ++o) load_gpatch(gO + ((long long)p.b * 2 + o) * 4 * hw, g, p, gv[o]);
-        const float* xp = x + ((long long)p.b * g.C + c0) * hw + (long long)p.y * g.W + p.x0;
-        const float4 t0 = ofr::ldg4(xp), t1 = two ? ofr::ldg4(xp + hw) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float xv[2][4] = {{t0.x, t0.y, t0.z, t0.w}, {t1.x, t1.y, t1.z, t1.w}};
-        if (pair == 0) {  // the patch's own outputs: rows 2y, 2y+1 (patch rows 1, 2), columns 2x0 .. 2x0+7 (1 .. 8)
-#pragma unroll
-            for (int o = 0; o < 2; ++o)
-#pragma unroll
-                for (int r = 1; r < 3; ++r)
-#pragma unroll
-                    for (int i = 1; i < 9; ++i) acc[64 + o] += gv[o][r][i];
+        for (int i = 0; i < 2; ++i) {  // rows 2*y0 - 1, 2*y0; the walk loads the other two
+            load_grow10(g0, 2 * y0 - 1 + i, X0, H2, W2, gv[0][i]);
+            load_grow10(g1, 2 * y0 - 1 + i, X0, H2, W2, gv[1][i]);
         }
+        for (int y = y0; y < y1; ++y) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            if (ch == 1 && !two) break;
+            for (int i = 2; i < 4; ++i) {
+                load_grow10(g0, 2 * y - 1 + i, X0, H2, W2, gv[0][i]);
+                load_grow10(g1, 2 * y - 1 + i, X0, H2, W2, gv[1][i]);
+            }
+            const float4 t0 = ofr::ldg4(xa + (long long)y * g.W);
+            const float4 t1 = two ? ofr::ldg4(xa + hw + (long long)y * g.W) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float xv[2][4] = {{t0.x, t0.y, t0.z, t0.w}, {t1.x, t1.y, t1.z, t1.w}};
+            if (pair == 0) {  // the patch's own outputs: rows 2y, 2y+1 (patch rows 1, 2), columns 2x0 .. 2x0+7 (1 .. 8)
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int r = 1; r < 3; ++r)
+#pragma unroll
+                        for (int i = 1; i < 9; ++i) acc[64 + o] += gv[o][r][i];
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                if (ch == 1 && !two) break;
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                acc[ch * 32 + o * 16 + ky * 4 + kx] = fmaf(xv[ch][i], gv[o][ky][2 * i + kx], acc[ch * 32 + o * 16 + ky * 4 + kx]);
+            }
 #pragma unroll
             for (int o = 0; o < 2; ++o)
 #pragma unroll
-                for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 4; ++kx)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            acc[ch * 32 + o * 16 + ky * 4 + kx] = fmaf(xv[ch][i], gv[o][ky][2 * i + kx], acc[ch * 32 + o * 16 + ky * 4 + kx]);
+                for (int j = 0; j < 10; ++j) gv[o][0][j] = gv[o][2][j], gv[o][1][j] = gv[o][3][j];
         }
     }
     warp_sum<66>(acc);
@@ -518,7 +616,8 @@ __global__ void __launch_bounds__(kThreads) deconv4_bwd_w_kernel(const float* __
 struct Plan {
     Geo g;
     int cper, ks;      // forward / input gradient: channels per CTA, channel splits
-    int wsplits;       // weight gradient: patch subsets
+    int wsplits;       // 3x3 weight gradient: subsets of the column groups
+    int wsplits4;      // transposed weight gradient: subsets of the row-patch groups
     int wwarps;        // weight gradient: channel pairs (warps) per CTA
     unsigned xblocks;  // ceil(items / kThreads)
 };
@@ -538,23 +637,26 @@ bool make_plan(Plan& p, int B, int C, int H, int W) {
     p.cper = (C + ks - 1) / ks;
     p.ks = (C + p.cper - 1) / p.cper;
     if (p.ks > 65535) return false;
-    // weight gradient: a warp per channel pair, wwarps (<= 4) pairs per CTA, wsplits patch subsets; ~32 warps per SM and
-    // every lane at least one patch
+    // weight gradient: a warp per channel pair, wwarps (<= 4) pairs per CTA, wsplits subsets of the lanes' work units (3x3:
+    // groups of 32 columns of walk_rows() row pairs; transposed: the same with walk_rows(H) input rows); ~32 warps per SM
     const int pairs = (C + 1) / 2;
     p.wwarps = pairs < kThreads / 32 ? pairs : kThreads / 32;
     const int pair_ctas = (pairs + p.wwarps - 1) / p.wwarps;
-    long long ws = (32ll * ofr::sm_count() / p.wwarps + pair_ctas - 1) / pair_ctas;
-    const long long max_ws = (p.g.items + 31) / 32;
-    if (ws > max_ws) ws = max_ws;
-    if (ws < 1) ws = 1;
-    if (ws > 65535) ws = 65535;
-    p.wsplits = (int)ws;
+    const long long want_ws = (32ll * ofr::sm_count() / p.wwarps + pair_ctas - 1) / pair_ctas;
+    const int wr = walk_rows(p.g.rp);
+    const long long groups3 = ((long long)B * ((p.g.rp + wr - 1) / wr) * p.g.gx + 31) / 32;
+    const int wr4 = walk_rows(H);
+    const long long groups4 = ((long long)B * ((H + wr4 - 1) / wr4) * p.g.gx + 31) / 32;
+    auto clamp_ws = [](long long ws, long long groups) { return (int)(ws > groups ? groups : ws < 1 ? 1 : ws > 65535 ? 65535 : ws); };
+    p.wsplits = clamp_ws(want_ws, groups3);
+    p.wsplits4 = clamp_ws(want_ws, groups4);
     return true;
 }
 
 size_t fwd_ws_bytes(const Plan& p, long long out_elems) { return p.ks > 1 ? sizeof(float) * (size_t)p.ks * out_elems : 0; }
 size_t wgrad_ws_bytes(const Plan& p, int K) {
-    return ofr::align_up(sizeof(float) * ((size_t)p.wsplits * p.g.C * 2 * K + (size_t)p.wsplits * 2), 256);
+    const size_t sp = K == 9 ? p.wsplits : p.wsplits4;
+    return ofr::align_up(sizeof(float) * (sp * p.g.C * 2 * K + sp * 2), 256);
 }
 
 }  // namespace
@@ -650,10 +752,10 @@ extern "C" int ofr_flowdeconv4_bwd(const float* x, const float* w, const float* 
     if (gW) {
         if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u) || ws_bytes < wgrad_ws_bytes(p, 16)) return OFR_EWORKSPACE;
         float* partial = (float*)ws;
-        float* pbias = partial + (size_t)p.wsplits * C * 32;
-        deconv4_bwd_w_kernel<<<dim3(((C + 1) / 2 + p.wwarps - 1) / p.wwarps, p.wsplits), 32 * p.wwarps, 0, st>>>(x, gO, partial, pbias, p.g, items, p.wsplits);
+        float* pbias = partial + (size_t)p.wsplits4 * C * 32;
+        deconv4_bwd_w_kernel<<<dim3(((C + 1) / 2 + p.wwarps - 1) / p.wwarps, p.wsplits4), 32 * p.wwarps, 0, st>>>(x, gO, partial, pbias, p.g, p.wsplits4);
         OFR_LAUNCH_CHECK();
-        wgrad_sum_kernel<<<(C * 32 + 2 + 7) / 8, 256, 0, st>>>(partial, pbias, gW, gB, C, 16, p.wsplits, 1);
+        wgrad_sum_kernel<<<(C * 32 + 2 + 7) / 8, 256, 0, st>>>(partial, pbias, gW, gB, C, 16, p.wsplits4, 1);
         OFR_LAUNCH_CHECK();
     }
     return OFR_OK;

@@ -35,10 +35,10 @@ for rep in sys.argv[1:]:
             try:
                 f = float(v.replace(",", ""))
                 unit = u.get(key, "")
-                if label.endswith("MB") and unit == "byte":
-                    f /= 1e6
-                if label == "dur us" and unit in ("nsecond", "ns"):
-                    f /= 1e3
+                if label.endswith("MB"):  # ncu picks the unit per value
+                    f *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}.get(unit, 1.0)
+                if label == "dur us":
+                    f *= {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6}.get(unit, 1.0)
                 v = f"{f:.4g}" if f < 1e6 else f"{f:.3e}"
             except ValueError:
                 pass
