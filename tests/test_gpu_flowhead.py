@@ -139,3 +139,39 @@ def test_accelerate_flow_heads_on_the_host_model(ofr):
             assert (a - b).abs().max().item() <= 2e-4 * max(1.0, float(b.abs().max()))
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_accelerate_flow_heads_on_the_reference_pwcdcnet(ofr):
+    """The reference's own ``PWCDCNet`` (PWC/models/PWCNet.py, unmodified, from baseline/_ref) with its flow heads
+    re-classed after construction: same state dict, same 7 flows in training mode, gradients reach every parameter."""
+    from ofr_b200.harness import reference_env, synthetic_pairs
+    if reference_env.reference_dir() is None:
+        pytest.skip("baseline/_ref not staged")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with reference_env.ReferenceEnv("ofr") as e:
+            torch.manual_seed(6)
+            net = e.pwcnet().to(DEV)
+            net.train()
+            keys = list(net.state_dict().keys())
+            x = synthetic_pairs(2, 128, seed=9).to(DEV)
+            with torch.no_grad():
+                ref = net(x)
+            changed = ofr.accelerate_flow_heads(net)
+            assert len(changed) == 5 + 1 + 6 + 4 and "deconv0" not in changed   # predict_flow6..2, dc_conv7, deconv6..1, upfeat6..3
+            assert list(net.state_dict().keys()) == keys
+            n0 = ofr.launch_count()
+            got = net(x)
+            assert ofr.launch_count() - n0 >= 9 + 16
+            assert len(got) == len(ref) == 7
+            for a, b in zip(got, ref):
+                assert (a - b).abs().max().item() <= 2e-4 * max(1.0, float(b.abs().max()))
+            sum(f.square().mean() for f in got).backward()
+            missing = [n for n, p_ in net.named_parameters() if p_.grad is None and not n.startswith("deconv0")]
+            assert not missing, missing
+            for n, p_ in net.named_parameters():
+                if p_.grad is not None:
+                    assert bool(torch.isfinite(p_.grad).all()), n
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
