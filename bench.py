@@ -41,6 +41,9 @@ TF32_MMA_PEAK_TFLOPS = 1096.0  # measured: profiles/r01_tf32_umma_micro.txt (tcg
 # shapes (B = 24, S = 512); keyed by the label of the C-ABI call
 NCU_TRAFFIC_BYTES = {
     "corr_bwd C32 128x128 D2=81 g2": (228.1e6 + 75.1e6, "profiles/r02_ncu_corr_bwd_box.txt"),
+    # ofr_flowconv3_bwd = conv3_bwd_x_kernel + conv3_bwd_w_kernel + wgrad_sum_kernel (reads + writes of the three)
+    "flowconv3_bwd C565 128x128": ((3.2 + 829.0 + 899.4 + 5.2 + 0.7) * 1e6, "profiles/r02_ncu_flow_heads.txt"),
+    "flowconv3_fwd C565 128x128": ((889.0 + 13.5 + 12.6) * 1e6, "profiles/r02_ncu_flow_heads.txt"),
     "corr_fwd C32 128x128 D9": (100.8e6 + 73.7e6, "profiles/r01_o_ncu_corr_fwd.txt"),
     "warp_bwd m2 C32 128x128 gI1=1 gI2=1": (107.0e6 + 30.9e6 + 3.2e6, "profiles/r01_t_ncu_corr_bwd_warp_bwd.txt"),
 }

@@ -32,7 +32,7 @@ class _FlowConv3Fn(torch.autograd.Function):
         out = torch.empty(B, 2, H, W, dtype=torch.float32, device=x.device)
         L = _lib.lib()
         ws = _workspace(L.ofr_flowconv3_workspace(B, C, H, W, 0), x.device)
-        with torch.cuda.device(x.device), region(f"flowconv3_fwd C{C} {H}x{W}", 4 * B * H * W * (C + 2)):
+        with torch.cuda.device(x.device), region(f"flowconv3_fwd C{C} {H}x{W}", 4 * B * H * W * (C + 2), 2 * 18 * B * C * H * W):
             _lib.check(L.ofr_flowconv3_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(out), B, C, H, W, _ptr(ws), ws.numel(),
                                            _stream()), "ofr_flowconv3_fwd")
         ctx.save_for_backward(x, weight)
@@ -50,7 +50,7 @@ class _FlowConv3Fn(torch.autograd.Function):
         gb = torch.empty(2, dtype=torch.float32, device=x.device) if need_w and ctx.has_bias else None
         L = _lib.lib()
         ws = _workspace(L.ofr_flowconv3_workspace(B, C, H, W, 1), x.device)
-        with torch.cuda.device(x.device), region(f"flowconv3_bwd C{C} {H}x{W}", 4 * B * H * W * (2 * C + 2)):
+        with torch.cuda.device(x.device), region(f"flowconv3_bwd C{C} {H}x{W}", 4 * B * H * W * (2 * C + 2), 4 * 18 * B * C * H * W):
             _lib.check(L.ofr_flowconv3_bwd(_ptr(x), _ptr(weight), _ptr(grad_out), _ptr(gx), _ptr(gw), _ptr(gb), B, C, H, W,
                                            _ptr(ws), ws.numel(), _stream()), "ofr_flowconv3_bwd")
         return gx, gw, gb
@@ -64,7 +64,7 @@ class _FlowDeconv4Fn(torch.autograd.Function):
         out = torch.empty(B, 2, 2 * H, 2 * W, dtype=torch.float32, device=x.device)
         L = _lib.lib()
         ws = _workspace(L.ofr_flowdeconv4_workspace(B, C, H, W, 0), x.device)
-        with torch.cuda.device(x.device), region(f"flowdeconv4_fwd C{C} {H}x{W}", 4 * B * H * W * (C + 8)):
+        with torch.cuda.device(x.device), region(f"flowdeconv4_fwd C{C} {H}x{W}", 4 * B * H * W * (C + 8), 2 * 32 * B * C * H * W):
             _lib.check(L.ofr_flowdeconv4_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(out), B, C, H, W, _ptr(ws), ws.numel(),
                                              _stream()), "ofr_flowdeconv4_fwd")
         ctx.save_for_backward(x, weight)
@@ -82,7 +82,7 @@ class _FlowDeconv4Fn(torch.autograd.Function):
         gb = torch.empty(2, dtype=torch.float32, device=x.device) if need_w and ctx.has_bias else None
         L = _lib.lib()
         ws = _workspace(L.ofr_flowdeconv4_workspace(B, C, H, W, 1), x.device)
-        with torch.cuda.device(x.device), region(f"flowdeconv4_bwd C{C} {H}x{W}", 4 * B * H * W * (2 * C + 8)):
+        with torch.cuda.device(x.device), region(f"flowdeconv4_bwd C{C} {H}x{W}", 4 * B * H * W * (2 * C + 8), 4 * 32 * B * C * H * W):
             _lib.check(L.ofr_flowdeconv4_bwd(_ptr(x), _ptr(weight), _ptr(grad_out), _ptr(gx), _ptr(gw), _ptr(gb), B, C, H, W,
                                              _ptr(ws), ws.numel(), _stream()), "ofr_flowdeconv4_bwd")
         return gx, gw, gb
