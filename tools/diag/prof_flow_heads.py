@@ -1,3 +1,5 @@
+"""Driver for `ncu -k regex:conv3_|deconv4_ ...`: two forward + backward passes of predict_flow2 (565 -> 2, 128^2) and upfeat3 (597 -> 2,
+64^2) at the bench batch (profiles/r02_ncu_flow_heads.txt)."""
 import sys, os
 sys.path.insert(0, "/root/repo")
 import torch, ofr_b200
