@@ -241,6 +241,7 @@ __host__ __device__ inline int walk_rows(int rp) { return rp >= 64 ? 16 : rp >= 
 // of the next patch are loaded before the arithmetic of this one.  The four warps of a CTA own four pairs and walk the
 // SAME columns: the gradient rows they all need come out of the L1 after the first warp has fetched them.  Pair 0 also
 // sums gO itself (bias gradient) into pbias[split][2].
+// (166 registers; capped at 128 for four CTAs per SM it spills and the backward of predict_flow2 goes from 556 to 781 us)
 __global__ void __launch_bounds__(kThreads) conv3_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gO,
                                                                float* __restrict__ partial, float* __restrict__ pbias,
                                                                Geo g, int splits) {
@@ -536,7 +537,9 @@ __device__ __forceinline__ void load_grow10(const float* __restrict__ plane, int
 // partial[split][c][o*16 + k] = sum over the split's row patches of x[c][y][x] * gO[o][2y - 1 + ky][2x - 1 + kx]; warps and
 // lanes as in conv3_bwd_w_kernel: a lane walks walk_rows(H) input rows down its 4-pixel column, and of the four gradient
 // rows 2y-1 .. 2y+2 it needs two are still in registers from the row above
-__global__ void __launch_bounds__(kThreads) deconv4_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gO,
+// three CTAs per SM: 200 -> 168 registers at the price of a 32-byte spill; upfeat3's backward 422 -> 350 us (four CTAs, 128
+// registers: 505 us)
+__global__ void __launch_bounds__(kThreads, 3) deconv4_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ gO,
                                                                  float* __restrict__ partial, float* __restrict__ pbias,
                                                                  Geo g, int splits) {
     const int lane = threadIdx.x & 31, pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
