@@ -85,6 +85,8 @@ __device__ __forceinline__ void stage_w3(float* ws, const float* __restrict__ w,
     }
 }
 
+// (95 / 149 registers for this kernel and deconv4_fwd_kernel; capped at 80 / 128 for six / four CTAs per SM both get slower:
+// predict_flow2 forward 338 -> 399 us, upfeat3 forward 172 -> 230 us)
 __global__ void __launch_bounds__(kThreads) conv3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              Geo g, int cper, int direct) {
