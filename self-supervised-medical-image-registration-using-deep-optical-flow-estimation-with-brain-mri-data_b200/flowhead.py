@@ -19,7 +19,9 @@ from .layers import _ptr, _stream, _workspace
 from .profiling import region
 
 
-def _fits(x, weight, transposed):
+def _fits(x, weight):
+    """Inputs the kernels take; anything else (CPU tensors, other dtypes, widths that are not a multiple of 4) stays with the
+    parent class."""
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[3] % 4 == 0 and
             weight.dtype == torch.float32 and weight.is_cuda and x.numel() > 0)
 
@@ -103,7 +105,7 @@ class FlowConv2d(nn.Conv2d):
     """``predict_flow`` (``PWC/models/PWCNet.py:30-31``): ``nn.Conv2d(C, 2, 3, 1, 1)`` with the 2-channel kernels."""
 
     def forward(self, x):
-        if _is_flow_conv(self) and _fits(x, self.weight, False):
+        if _is_flow_conv(self) and _fits(x, self.weight):
             return _FlowConv3Fn.apply(x, self.weight, self.bias)
         return super().forward(x)
 
@@ -112,7 +114,7 @@ class FlowUpsample2d(nn.ConvTranspose2d):
     """``deconv`` (``PWC/models/PWCNet.py:33-34``): ``nn.ConvTranspose2d(C, 2, 4, 2, 1)`` with the 2-channel kernels."""
 
     def forward(self, x, output_size=None):
-        if output_size is None and _is_flow_deconv(self) and _fits(x, self.weight, True):
+        if output_size is None and _is_flow_deconv(self) and _fits(x, self.weight):
             return _FlowDeconv4Fn.apply(x, self.weight, self.bias)
         return super().forward(x, output_size)
 

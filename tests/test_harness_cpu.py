@@ -196,3 +196,31 @@ def test_bench_reference_arm_is_same_config_by_default():
     bench = importlib.import_module("bench")
     src = open(bench.__file__).read()
     assert '"--cpu-batch", type=int, default=0' in src and '"same_config": batch == args.batch' in src
+
+
+def test_flow_heads_reclass_in_place_and_fall_back_on_cpu():
+    """``accelerate_flow_heads`` on the CPU: only the two-output-channel 3x3 / 4x4-stride-2 layers change class,
+    parameters and state-dict keys stay, and a CPU tensor goes through the parent ``nn`` forward (the kernels are CUDA-only;
+    this is the reference's own op, not a fallback of the product path)."""
+    import torch.nn as nn
+    import ofr_b200
+    from ofr_b200.harness import PWCNetHost
+    torch.manual_seed(0)
+    net = PWCNetHost(md=4, fast_heads=False)
+    keys = list(net.state_dict().keys())
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    changed = ofr_b200.accelerate_flow_heads(net)
+    assert sorted(changed) == sorted([f"predict_flow{i}" for i in (6, 5, 4, 3, 2)] + ["dc_conv7"] +
+                                     [f"deconv{i}" for i in (6, 5, 4, 3, 2, 1)] + [f"upfeat{i}" for i in (6, 5, 4, 3)])
+    assert type(net.deconv0) is nn.ConvTranspose2d and type(net.conv1a[0]) is nn.Conv2d
+    assert isinstance(net.predict_flow2, ofr_b200.FlowConv2d) and isinstance(net.upfeat3, ofr_b200.FlowUpsample2d)
+    assert list(net.state_dict().keys()) == keys
+    assert all(torch.equal(v, before[k]) for k, v in net.state_dict().items())
+    assert ofr_b200.accelerate_flow_heads(net) == []                      # idempotent
+    x = torch.randn(2, net.predict_flow6.in_channels, 4, 4)
+    assert torch.equal(net.predict_flow6(x), torch.nn.functional.conv2d(x, net.predict_flow6.weight, net.predict_flow6.bias, 1, 1))
+    f = torch.randn(2, 2, 4, 4)
+    assert torch.equal(net.deconv6(f), torch.nn.functional.conv_transpose2d(f, net.deconv6.weight, net.deconv6.bias, 2, 1))
+    fresh = PWCNetHost(md=4)                                              # product default: heads re-classed at construction
+    assert isinstance(fresh.dc_conv7, ofr_b200.FlowConv2d)
+    fresh.load_state_dict(net.state_dict())
