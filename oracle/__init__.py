@@ -27,14 +27,19 @@ Parity pinning status (see DESIGN.md "Oracle"):
   and (ii) ``F.grid_sample(padding_mode='border', align_corners=True)`` for the
   clamped bilinear gather; fixtures from both are committed under
   ``tests/golden/``.
+* ``flowhead_ref.predict_flow`` / ``deconv`` ARE the reference's ops: it builds these layers from
+  ``torch.nn`` (``PWC/models/PWCNet.py:30-34``).  PINNED by construction; the loop restatements beside them fix the
+  index conventions the CUDA kernels implement.
 """
 from .layers_ref import (correlation, correlation_loops, resample2d, resample2d_loops,
                          channelnorm, channelnorm_backward, correlation_out_shape, MODULES, Correlation_like)
 from .warp_ref import stn_warp, pwc_warp, pixel_grid
 from .loss_ref import (charbonnier, photometric, smoothness, ncc, ofe_loss)
+from .flowhead_ref import predict_flow, deconv, predict_flow_loops, deconv_loops
 
 __all__ = [
     "correlation", "correlation_loops", "correlation_out_shape", "resample2d", "resample2d_loops",
     "channelnorm", "channelnorm_backward", "stn_warp", "pwc_warp", "pixel_grid",
     "charbonnier", "photometric", "smoothness", "ncc", "ofe_loss", "MODULES", "Correlation_like",
+    "predict_flow", "deconv", "predict_flow_loops", "deconv_loops",
 ]

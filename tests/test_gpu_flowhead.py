@@ -1,10 +1,13 @@
 """GPU: the two-output-channel layers of the PWC-Net decoder -- ``predict_flow`` = nn.Conv2d(C, 2, 3, 1, 1)
-and ``deconv`` / ``upfeat`` = nn.ConvTranspose2d(C, 2, 4, 2, 1) (PWC/models/PWCNet.py:30-34) -- against PyTorch's own
-float64 CPU convolutions (the reference's implementation of these layers IS ``torch.nn``), values and all gradients."""
+and ``deconv`` / ``upfeat`` = nn.ConvTranspose2d(C, 2, 4, 2, 1) (PWC/models/PWCNet.py:30-34) -- against the oracle
+(``oracle/flowhead_ref.py``: the reference's implementation of these layers IS ``torch.nn``, run here in float64 on the
+CPU), values and all gradients."""
 import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+import oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -45,7 +48,7 @@ def test_flow_conv3_matches_torch_float64(ofr, shape, bias):
     xr = x.double().requires_grad_(True)
     wr = m.weight.detach().double().requires_grad_(True)
     br = m.bias.detach().double().requires_grad_(True) if bias else None
-    ref = F.conv2d(xr, wr, br, 1, 1)
+    ref = oracle.predict_flow(xr, wr, br)
     grads_ref = torch.autograd.grad(ref, [xr, wr] + ([br] if bias else []), go.double())
     m = m.to(DEV)
     xd = x.to(DEV).requires_grad_(True)
@@ -72,7 +75,7 @@ def test_flow_deconv4_matches_torch_float64(ofr, shape, bias):
     xr = x.double().requires_grad_(True)
     wr = m.weight.detach().double().requires_grad_(True)
     br = m.bias.detach().double().requires_grad_(True) if bias else None
-    ref = F.conv_transpose2d(xr, wr, br, 2, 1)
+    ref = oracle.deconv(xr, wr, br)
     grads_ref = torch.autograd.grad(ref, [xr, wr] + ([br] if bias else []), go.double())
     m = m.to(DEV)
     xd = x.to(DEV).requires_grad_(True)

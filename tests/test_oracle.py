@@ -205,3 +205,18 @@ def test_ncc_constant_images_vs_reference_golden(golden):
         assert abs(got - want) <= 1e-6, (v, got, want)
         assert (want == 0.0) == bool(zero)
     assert g["ref_loss"][3] > 0.99   # 0.7: float32 rounding noise decides in the reference
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 6, 8), (1, 3, 1, 4), (2, 2, 7, 5)])
+def test_flow_head_loop_restatements_equal_torch_convolutions(shape):
+    """the reference's flow heads are ``nn.Conv2d(C, 2, 3, 1, 1)`` / ``nn.ConvTranspose2d(C, 2, 4, 2, 1)``
+    (PWCNet.py:30-34); the explicit shifted-sum statements in oracle/flowhead_ref.py agree with PyTorch's ops in float64."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    w3 = torch.randn(2, C, 3, 3, generator=g, dtype=torch.float64)
+    w4 = torch.randn(C, 2, 4, 4, generator=g, dtype=torch.float64)
+    b = torch.randn(2, generator=g, dtype=torch.float64)
+    assert (oracle.predict_flow_loops(x, w3, b) - oracle.predict_flow(x, w3, b)).abs().max().item() < 1e-12
+    assert (oracle.deconv_loops(x, w4, b) - oracle.deconv(x, w4, b)).abs().max().item() < 1e-12
+    assert oracle.deconv(x, w4).shape == (B, 2, 2 * H, 2 * W)
