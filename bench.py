@@ -389,6 +389,11 @@ def run_ours(args):
                     "hot_path_algorithmic_bytes": sum(r["algorithmic_bytes"] * r["calls_per_step"] for r in rows),
                     "hot_path_hbm_frac": round(sum(r["algorithmic_bytes"] * r["calls_per_step"] for r in rows)
                                                / (ours_ms * 1e-3) / 1e9 / peak, 4) if ours_ms > 0 else None}
+        if dom["kernel"].startswith("flow"):
+            # a flow-head row is one C-ABI call, i.e. up to three launches; the per-kernel ncu figures are in the profile
+            roofline["note"] = ("row = one ofr_flow*_{fwd,bwd} call (forward: channel-split kernel + split sum; backward: "
+                                "input-gradient kernel + weight-gradient kernel + split sum); per-kernel durations and "
+                                "DRAM bytes: profiles/r02_ncu_flow_heads.txt")
         secondary = None
         if world == 1 and args.secondary:
             try:
