@@ -7,6 +7,7 @@ Sources of truth, none of them modified:
   * /root/reference/PWC/models/PWCNet.py -> warps.npz (PWCDCNet.warp)
   * TVM's numpy ``correlation_nchw_python`` (ships in this image's site-packages) -> corr.npz
   * torch ``F.grid_sample(padding_mode='border', align_corners=True)``           -> resample.npz
+  * /root/reference/PWC/models/PWCNet.py ``predict_flow`` / ``deconv`` helpers    -> flowhead.npz (--only-flowhead)
 
 The reference modules need a few absent third-party imports stubbed (monai,
 matplotlib, skimage, torchmetrics, RAFT, the custom CUDA layers); the stubs are
@@ -221,8 +222,37 @@ def make_ncc_const(ref_loss):
     return out
 
 
+def make_flowhead(ref_pwc):
+    """flowhead.npz: the reference's own helpers ``predict_flow(in_planes)`` and ``deconv(in_planes, 2)``
+    (PWC/models/PWCNet.py:30-34) construct the layers; inputs, parameters, outputs and all gradients of two shapes each,
+    float32 on the CPU exactly as the reference module computes them."""
+    g = torch.Generator().manual_seed(68)
+    out = {}
+    for tag, (B, C, H, W) in {"a": (2, 5, 6, 8), "b": (1, 37, 9, 12)}.items():
+        for kind, layer in (("conv", ref_pwc.predict_flow(C)), ("deconv", ref_pwc.deconv(C, 2))):
+            with torch.no_grad():
+                layer.weight.copy_(torch.randn(layer.weight.shape, generator=g) / (3.0 * C ** 0.5))
+                layer.bias.copy_(torch.randn(2, generator=g))
+            x = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+            y = layer(x)
+            go = torch.randn(y.shape, generator=g)
+            gx, gw, gb = torch.autograd.grad(y, (x, layer.weight, layer.bias), go)
+            k = f"{kind}_{tag}_"
+            out.update({k + "x": x.detach().numpy(), k + "w": layer.weight.detach().numpy(), k + "b": layer.bias.detach().numpy(),
+                        k + "y": y.detach().numpy(), k + "go": go.numpy(), k + "gx": gx.numpy(), k + "gw": gw.numpy(),
+                        k + "gb": gb.numpy()})
+    np.savez_compressed(os.path.join(HERE, "flowhead.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
-    if "--only-ncc-const" in sys.argv:
+    if "--only-flowhead" in sys.argv:
+        sys.path.insert(0, REF)
+        sys.path.insert(0, os.path.join(REF, "PWC", "models"))
+        _install_stubs()
+        o = make_flowhead(importlib.import_module("PWCNet"))
+        print("wrote flowhead.npz", sorted(o)[:4], "...")
+    elif "--only-ncc-const" in sys.argv:
         sys.path.insert(0, REF)
         _install_stubs()
         _loss = importlib.import_module("loss")

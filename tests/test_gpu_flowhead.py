@@ -178,3 +178,23 @@ def test_accelerate_flow_heads_on_the_reference_pwcdcnet(ofr):
                     assert bool(torch.isfinite(p_.grad).all()), n
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("kind,tag", [("conv", "a"), ("conv", "b"), ("deconv", "a"), ("deconv", "b")])
+def test_flow_heads_vs_reference_golden(ofr, golden, kind, tag):
+    """The kernels against what the reference's own ``predict_flow`` / ``deconv`` layers computed (flowhead.npz)."""
+    g = golden("flowhead")
+    k = f"{kind}_{tag}_"
+    x, w, b, go = (torch.from_numpy(g[k + n]).to(DEV) for n in ("x", "w", "b", "go"))
+    C = x.shape[1]
+    m = (ofr.FlowConv2d(C, 2, 3, 1, 1) if kind == "conv" else ofr.FlowUpsample2d(C, 2, 4, 2, 1)).to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(w)
+        m.bias.copy_(b)
+    xd = x.clone().requires_grad_(True)
+    n0 = ofr.launch_count()
+    y = m(xd)
+    assert ofr.launch_count() > n0
+    gx, gw, gb = torch.autograd.grad(y, (xd, m.weight, m.bias), go)
+    for name, got, ref in (("y", y, g[k + "y"]), ("gx", gx, g[k + "gx"]), ("gw", gw, g[k + "gw"]), ("gb", gb, g[k + "gb"])):
+        _check(f"{kind}_{tag} {name}", got, torch.from_numpy(ref), rtol=2e-5)

@@ -220,3 +220,18 @@ def test_flow_head_loop_restatements_equal_torch_convolutions(shape):
     assert (oracle.predict_flow_loops(x, w3, b) - oracle.predict_flow(x, w3, b)).abs().max().item() < 1e-12
     assert (oracle.deconv_loops(x, w4, b) - oracle.deconv(x, w4, b)).abs().max().item() < 1e-12
     assert oracle.deconv(x, w4).shape == (B, 2, 2 * H, 2 * W)
+
+
+@pytest.mark.parametrize("kind,tag", [("conv", "a"), ("conv", "b"), ("deconv", "a"), ("deconv", "b")])
+def test_flow_head_oracle_vs_reference_golden(golden, kind, tag):
+    """flowhead.npz holds what the reference's own ``predict_flow`` / ``deconv`` layers (PWCNet.py:30-34) computed on the
+    CPU in float32 (tests/golden/make_golden.py --only-flowhead); the oracle, run in float64, agrees to float32 rounding."""
+    g = golden("flowhead")
+    k = f"{kind}_{tag}_"
+    x, w, b, go = (torch.from_numpy(g[k + n]).double() for n in ("x", "w", "b", "go"))
+    x.requires_grad_(True), w.requires_grad_(True), b.requires_grad_(True)
+    y = (oracle.predict_flow if kind == "conv" else oracle.deconv)(x, w, b)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), go)
+    for name, got, ref in (("y", y, g[k + "y"]), ("gx", gx, g[k + "gx"]), ("gw", gw, g[k + "gw"]), ("gb", gb, g[k + "gb"])):
+        ref = torch.from_numpy(ref).double()
+        assert (got.detach() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), name
